@@ -1,0 +1,24 @@
+"""Helpers to read the frozen reference traces in tests/golden (format: tests/golden/make_golden.py)."""
+import glob
+import os
+import zlib
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_files():
+    return sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    d = {k: z[k] for k in z.files}
+    for k in ("H", "W", "max_steps", "subset"):
+        d[k] = int(d[k])
+    return d
+
+
+def crc(img) -> int:
+    return zlib.crc32(np.ascontiguousarray(img, dtype=np.uint8).tobytes()) & 0xFFFFFFFF
