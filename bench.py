@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched CraftingWorld hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of worlds: ONE fused step + auto-reset + render launch
+(cw_env_kernel) per step for the pixel workloads, one cw_step_kernel launch for the compact workload.  Worlds are
+sharded over ranks by global id with no data-path collective (weak scaling: per-GPU batch fixed); with N > 1 the
+24 x int64 episode-statistics vector is all-reduced over NCCL every 128 steps on a side stream.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (actions already in HBM, frames left in HBM);
+`e2e` is the same metric through the host-buffer C entry points (cw_host_step: pinned host actions -> device ->
+fused launches -> frames, reward, done back to pinned host memory); `roofline` is the fused kernel's algorithmic
+bytes per launch / its mean launch duration against the measured HBM copy bandwidth; `cpu_baseline` times the CPU
+port of the reference's env loop on this box's host cores.  `--impl reference` times only that CPU port.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec w/ pixel obs"
+UNIT = "env-steps/s"
+TAPE = 128                      # length of the pre-generated action tape == steps per CUDA graph == stats period
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1
+    "cfg2": dict(envs=4096, size=21, obs="pixels", dense=False,
+                 desc="4096 envs default 21x21 grid per GPU, pixel obs, nine-skill random tasks, auto-reset"),
+    "cfg3": dict(envs=65536, size=21, obs="compact", dense=False,
+                 desc="65536 envs default grid per GPU, compact-state obs (no render), step kernel only"),
+    "cfg4": dict(envs=131072, size=21, obs="pixels", dense=False,
+                 desc="131072 envs default grid per GPU (1M over 8), pixel obs, stats all-reduce every 128 steps"),
+    "cfg5": dict(envs=16384, size=32, obs="pixels", dense=True,
+                 desc="16384 envs 32x32 grid per GPU, dense object placement, pixel obs"),
+}
+
+
+def algorithmic_bytes(size, obs):
+    """bytes one env-step must move.  pixels: frame write + grid read + 32 B scalars; compact: 32 B."""
+    return 48 * size * size + size * size + 32 if obs == "pixels" else 32
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the Python port of the reference env loop (oracle/pyenv.py), one process per host core
+# ---------------------------------------------------------------------------------------------------------
+def cpu_port_throughput(size, envs_per_proc, steps, warmup, procs=None):
+    import multiprocessing as mp
+    from oracle import pyenv
+    cores = sorted(os.sched_getaffinity(0))
+    procs = procs or len(cores)
+    ctx = mp.get_context("fork")
+    args = [(envs_per_proc, steps, warmup, (size, size), 300, 1000 + i) for i in range(procs)]
+    with ctx.Pool(procs) as pool:
+        res = pool.map(pyenv.run_worker, args)
+    total = sum(n for n, _ in res)
+    slowest = max(dt for _, dt in res)
+    return total / slowest, procs, total
+
+
+def cpu_c_port_throughput(size, envs, steps, render_mode, threads):
+    """The C restatement (oracle/cw_oracle.c) on `threads` pthreads: a much stronger CPU baseline than the reference's
+    own Python loop; reported beside it for context."""
+    import numpy as np
+    from oracle import native
+    ob = native.OracleBatch(native.make_config(H=size, W=size), envs, seed=1)
+    ob.reset()
+    obs = ob.render() if render_mode else None
+    acts = np.random.RandomState(0).randint(0, 6, (steps, envs)).astype(np.uint8)
+    ob.run_threads(acts[:2], render_mode=render_mode, obs=obs, nthreads=threads)
+    t0 = time.perf_counter()
+    ob.run_threads(acts, render_mode=render_mode, obs=obs, nthreads=threads)
+    return envs * steps / (time.perf_counter() - t0)
+
+
+def cpu_baseline_block(size, quick=False):
+    cores = len(os.sched_getaffinity(0))
+    steps = 1500 if quick else 6000
+    v, procs, total = cpu_port_throughput(size, 16, steps, 100)
+    out = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+           "sample": f"{procs} processes x 16 worlds x {steps} steps ({total} env-steps) of the {size}x{size} nine-skill "
+                     f"env loop, Python/NumPy port of the reference (oracle/pyenv.py: incremental render_edit, reset on done)"}
+    try:
+        k = 40 if quick else 150
+        out["c_port"] = {
+            "incremental_render": cpu_c_port_throughput(size, 4096, k * 4, 2, cores),
+            "full_render_every_step": cpu_c_port_throughput(size, 4096, k, 1, cores),
+            "unit": UNIT, "cores": cores,
+            "note": "oracle/cw_oracle.c on pthreads (not the reference's implementation language); context only"}
+    except Exception as e:  # noqa: BLE001
+        out["c_port"] = {"error": repr(e)}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1, t_load0):
+        def parse(rows):
+            sm, mx, reasons = [], 0.0, set()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for _, line in rows:
+                p = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(p[0])); mx = max(mx, float(p[1]))
+                except (ValueError, IndexError):
+                    continue
+                for nm, val in zip(names, p[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, sorted(reasons)
+        timed = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed region"
+        if len(timed) < 3:
+            timed = [s for s in self.samples if t_load0 <= s[0] <= t1 + 0.3]
+            window = "warm-up + timed region (timed region shorter than 3 samples)"
+        sm, mx, reasons = parse(timed)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "window": window}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth, burst)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(workload):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def dense_worlds(env, torch, seed):
+    """BASELINE config 5 placement: each non-agent cell occupied w.p. 0.5, type uniform over the 8 objects, >= 1 of
+    each type, agent on an empty cell, nothing held."""
+    N, H, W = env.num_envs, env.cfg.H, env.cfg.W
+    g = torch.Generator(device=env.device).manual_seed(seed)
+    occ = torch.rand((N, H * W), generator=g, device=env.device) < 0.5
+    typ = torch.randint(1, 9, (N, H * W), generator=g, device=env.device, dtype=torch.uint8)
+    grid = torch.where(occ, typ, torch.zeros_like(typ))
+    cells = torch.rand((N, H * W), generator=g, device=env.device).argsort(dim=1)[:, :9]
+    for k in range(8):
+        grid.scatter_(1, cells[:, k:k + 1], torch.full((N, 1), k + 1, dtype=torch.uint8, device=env.device))
+    ac = cells[:, 8]
+    grid.scatter_(1, ac.unsqueeze(1), torch.zeros((N, 1), dtype=torch.uint8, device=env.device))
+    desired = torch.randint(1, 512, (N,), generator=g, device=env.device)
+    env.load_state(grid.cpu().numpy().reshape(N, H, W), (ac // W).cpu().numpy(), (ac % W).cpu().numpy(),
+                   torch.zeros(N).numpy(), desired.cpu().numpy())
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import gym_craftingworld_b200 as cw
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs:
+        wl["envs"] = args.envs
+    K, W_ = args.steps, max(args.warmup, 3)
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:                  # before CUDA is initialised (fork-safe)
+        cpu_base = cpu_baseline_block(wl["size"], quick=args.quick)
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, size = wl["envs"], wl["size"]
+    pixels = wl["obs"] == "pixels"
+    frame_bytes = 48 * size * size
+    ring = 1
+    if pixels:                                                   # rotate frame buffers so the ring exceeds the 126 MB L2
+        while N * frame_bytes * ring < 300e6 and ring < 64:
+            ring *= 2
+    env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=dev, auto_reset=True, obs_mode=wl["obs"],
+                                     env_id_base=rank * N, obs_buffers=ring)
+    env.reset()
+    if wl["dense"]:
+        dense_worlds(env, torch, 99 + rank)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    tape = torch.randint(0, 6, (TAPE, N), generator=gen, device=dev, dtype=torch.uint8)
+    reducer = cw.StatsReducer(env.stats, every=TAPE) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    t_load0 = time.perf_counter()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    with torch.cuda.stream(stream):
+        for k in range(W_):                                      # eager warm-up (also warms the launch path)
+            env.step(tape[k % TAPE])
+        torch.cuda.synchronize()
+
+        def capture(nsteps):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for k in range(nsteps):
+                    env.step(tape[k])
+            return g
+        n_full, rem = divmod(K, TAPE)
+        g_full = capture(TAPE) if n_full else None
+        g_rem = capture(rem) if rem else None
+        for g in (g_full, g_rem):                                # one untimed replay each (extra warm-up)
+            if g is not None:
+                g.replay()
+        torch.cuda.synchronize()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(n_full):
+            g_full.replay()
+            if reducer is not None:
+                reducer.reduce_async()                           # every 128 steps, on a side stream
+        if g_rem is not None:
+            g_rem.replay()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        if reducer is not None:
+            reducer.wait()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    stats_local = env.episode_stats()
+
+    # ---- end to end through the host-buffer C entry points --------------------------------------------------
+    e2e = {}
+    if pixels and not args.no_e2e:
+        e_steps = max(10, min(K, 200 if not args.quick else 20))
+        if N * frame_bytes > 1.5e9:
+            e_steps = min(e_steps, 10)
+        res = {}
+        for frames in (True, False):
+            henv = cw.HostCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=local_rank, env_id_base=rank * N,
+                                           return_frames=frames)
+            henv.reset()
+            acts = tape.cpu().numpy()
+            for k in range(3):
+                henv.step(acts[k])
+            barrier()
+            h0 = time.perf_counter()
+            for k in range(e_steps):
+                henv.step(acts[k % TAPE])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - h0
+            if world > 1:
+                tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            res[frames] = (N * world * e_steps / dt, henv.h2d_bytes_per_step, henv.d2h_bytes_per_step)
+            henv.close()
+            barrier()
+        e2e = {"value": res[True][0], "unit": UNIT, "h2d_bytes_per_step": res[True][1], "d2h_bytes_per_step": res[True][2],
+               "steps": e_steps, "api": "HostCraftingWorldEnv.step -> cw_host_step (pinned host actions in; frames, reward, done out)",
+               "frames_left_on_device": {"value": res[False][0], "d2h_bytes_per_step": res[False][2],
+                                         "note": "same call with obs_host=NULL: pixels stay in HBM for a device-side consumer"}}
+    if sampler:
+        sampler.stop()
+
+    if rank == 0:
+        secs = ms / 1e3
+        value = N * world * K / secs
+        peak, peak_src = measured_peak()
+        B = algorithmic_bytes(size, wl["obs"])
+        launch_s = secs / K
+        achieved = B * N / launch_s / 1e9
+        line = {
+            "metric": METRIC if pixels else "env-steps/sec compact obs (step kernel only)", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "envs_per_gpu": N, "grid": f"{size}x{size}", "obs": wl["obs"],
+                       "actions": "uniform iid over 6 actions, pre-generated uint8[128,N] tape on device, cycled",
+                       "launch": f"CUDA graphs of {TAPE} steps, one fused launch per step",
+                       "l2": (f"frames written round-robin into {ring} buffers = {ring * N * frame_bytes / 1e6:.0f} MB > 126 MB L2 "
+                              "(inputs larger than L2; no flush needed)") if pixels else "state 65536 x ~0.9 KB; step kernel is latency bound",
+                       "parallelism": f"dp{world} (worlds sharded by global id, no data-path collective)"},
+            "clocks": sampler.summary(t0, t1, t_load0) if sampler else None,
+            "gpu_launches": K,
+            "e2e": e2e or None,
+            "roofline": {"bound": "hbm", "kernel": "cw_env_kernel" if pixels else "cw_step_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                         "algorithmic_bytes_per_env_step": B, "units_per_launch": N, "launch_us": launch_s * 1e6,
+                         "peak_source": peak_src,
+                         "note": "launch duration = CUDA-event time of the timed region / launches (includes inter-kernel gaps)"},
+            "cpu_baseline": cpu_base,
+            "episode_stats_rank0": {k: stats_local[k] for k in ("episodes", "successes", "mean_return", "mean_length")},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference arm: the CPU port of the reference env loop on all host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    K, W_ = args.steps, max(args.warmup, 3)
+    cores = len(os.sched_getaffinity(0))
+    # a "step" steps every world of the bounded sample once: `per_proc` worlds per process, sized from a short
+    # calibration so that K steps take roughly 15 s of wall clock (never more than a few minutes)
+    rate, _, _ = cpu_port_throughput(wl["size"], 8, 200, 20, procs=cores)
+    per_proc = int(max(1, min(2048, rate / cores * 15.0 / max(K, 1))))
+    value, procs, total = cpu_port_throughput(wl["size"], per_proc, K, W_, procs=cores)
+    sample = (f"{procs} processes x {per_proc} worlds, one step = every world stepped once ({procs * per_proc} env-steps), "
+              f"{wl['size']}x{wl['size']} nine-skill env loop with reset on done; Python/NumPy port of the reference "
+              "(oracle/pyenv.py) -- the reference itself cannot be imported on this box (no gym / matplotlib)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": K, "warmup": W_, "ms_per_step": 1e3 * procs * per_proc / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']} (bounded CPU sample)", "grid": f"{wl['size']}x{wl['size']}"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=51200)
+    ap.add_argument("--warmup", type=int, default=256)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override worlds per GPU")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--quick", action="store_true", help="shorter CPU baseline / e2e legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

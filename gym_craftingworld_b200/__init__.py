@@ -1,0 +1,17 @@
+"""gym_craftingworld_b200 -- B200-native batched CraftingWorld (the env hot path of lauradarcy/gym-craftingworld).
+
+Importing the package builds (if stale) and loads ``libcw_b200.so``; there is no CPU fallback -- if the CUDA
+library cannot be built or loaded the import raises.
+"""
+from . import _lib
+
+_lib.load()   # fail loudly at import time
+
+from .env import (ACTION_NAMES, COLORS_N, MAX_STEPS, OBJECTS, PICKUPABLE, TASK_LIST,  # noqa: E402
+                  BatchedCraftingWorldEnv, make_config)
+from .host_env import HostCraftingWorldEnv  # noqa: E402
+from .dist import StatsReducer, shard_range  # noqa: E402
+
+__all__ = ["BatchedCraftingWorldEnv", "HostCraftingWorldEnv", "StatsReducer", "shard_range", "make_config", "TASK_LIST",
+           "OBJECTS", "PICKUPABLE", "ACTION_NAMES", "COLORS_N", "MAX_STEPS"]
+__version__ = "0.1.0"

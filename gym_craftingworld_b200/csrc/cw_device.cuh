@@ -1,0 +1,410 @@
+// cw_device.cuh -- device-side building blocks of the batched CraftingWorld hot path (sm_100a).
+//
+// Semantics follow the reference env, gym_craftingworld/envs/craftingworld_ray.py ("ray.py") and
+// envs/coordinates.py; the citations beside each block are the lines it re-implements for N worlds.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cw_b200.h"
+
+namespace cw {
+
+enum : int { EMPTY = 0, STICKS, AXE, HAMMER, ROCK, TREE, BREAD, HOUSE, WHEAT };  // ray.py:21 (+1)
+enum : int {                                                                      // ray.py:40-41
+    T_MAKE_BREAD = 0, T_EAT_BREAD, T_BUILD_HOUSE, T_CHOP_TREE, T_CHOP_ROCK, T_GO_TO_HOUSE, T_MOVE_AXE,
+    T_MOVE_HAMMER, T_MOVE_STICKS
+};
+
+// COLORS_N (ray.py:28-30) packed R | G<<8 | B<<16
+#define CW_RGB(r, g, b) ((uint32_t)(r) | ((uint32_t)(g) << 8) | ((uint32_t)(b) << 16))
+__device__ __constant__ uint32_t kColorLUT[9] = {
+    CW_RGB(0, 0, 0),       CW_RGB(110, 69, 39),  CW_RGB(255, 105, 180), CW_RGB(100, 100, 200), CW_RGB(100, 100, 100),
+    CW_RGB(0, 128, 0),     CW_RGB(205, 133, 63), CW_RGB(197, 91, 97),   CW_RGB(240, 230, 140)};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ------------------------------------------------------------------------------------------------------
+// Philox4x32-10, warp-replicated stream.  Stream layout (the spec is oracle/compact.py PhiloxStream):
+// key = (seed_lo, seed_hi), counter = (env_lo, env_hi, episode, block), words of a block consumed in order.
+// Lane l holds block (base + l), so one refill yields 128 words; every lane tracks the same position and
+// sees the same draws, so all control flow on the draws is warp-uniform.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                              uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+struct WarpPhilox {
+    uint32_t k0, k1, e0, e1, ep, base;
+    uint32_t w0, w1, w2, w3;
+    int pos;  // 0..128
+
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t env_id, uint32_t episode) {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        e0 = (uint32_t)env_id; e1 = (uint32_t)(env_id >> 32); ep = episode;
+        base = 0; pos = 128;
+    }
+    __device__ __forceinline__ void refill() {
+        w0 = e0; w1 = e1; w2 = ep; w3 = base + (uint32_t)lane_id();
+        philox4x32_10(w0, w1, w2, w3, k0, k1);
+        base += 32; pos = 0;
+    }
+    __device__ __forceinline__ uint32_t next32() {
+        if (pos == 128) refill();
+        const int j = pos & 3;
+        const uint32_t mine = j == 0 ? w0 : (j == 1 ? w1 : (j == 2 ? w2 : w3));
+        const uint32_t v = __shfl_sync(0xffffffffu, mine, pos >> 2);
+        pos++;
+        return v;
+    }
+    // unbiased integer in [0,n): Lemire multiply-shift with rejection
+    __device__ __forceinline__ uint32_t uniform(uint32_t n) {
+        uint64_t m = (uint64_t)next32() * n;
+        uint32_t lo = (uint32_t)m;
+        if (lo < n) {
+            const uint32_t thresh = (0u - n) % n;
+            while (lo < thresh) { m = (uint64_t)next32() * n; lo = (uint32_t)m; }
+        }
+        return (uint32_t)(m >> 32);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// step(action): ray.py:301-378.  `g` is this world's grid (global or shared), `ig` its initial grid (global).
+// All cell reads are issued up front (no dependent load chain); at most one cell is written.
+// Returns the reward; done/changed by reference.  `wcell`/`wval` report the single grid write (wcell < 0: none)
+// so a caller that steps on a shared-memory copy can mirror it to global memory.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t setbit(uint32_t m, int bit, bool on) {
+    return on ? (m | (1u << bit)) : (m & ~(1u << bit));
+}
+
+__device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restrict__ g, const uint8_t* __restrict__ ig,
+                                         uint32_t& agent, uint32_t& goal, int& t, int a, bool& done, int& wcell,
+                                         int& wval) {
+    const int W = cfg.W, H = cfg.H, M = cfg.max_steps;
+    int r = agent & 0xFF, c = (agent >> 8) & 0xFF, h = (agent >> 16) & 0xFF;
+    uint32_t ach = goal & 0xFFFFu;
+    const uint32_t des = goal >> 16;
+    t += 1;                                                                      // ray.py:309
+    wcell = -1; wval = 0;
+    bool changed;
+    const int cell = r * W + c;
+    if (a >= 4) {
+        const int here = g[cell];
+        if (a == 4) {                                                            // pickup, ray.py:314-327
+            changed = (here >= STICKS) & (here <= HAMMER) & (h == 0);            // ray.py:317-322
+            if (changed) { h = here; wcell = cell; wval = EMPTY; }               // ray.py:326-327
+        } else if (a == 5) {                                                     // drop, ray.py:329-341
+            changed = (h != 0) & (here == EMPTY);                                // ray.py:332-335
+            if (changed) { wcell = cell; wval = h; h = 0; }                      // ray.py:339-341
+        } else {
+            changed = false;  // out-of-range action: defined no-op (reference: IndexError, ray.py:308)
+        }
+    } else {                                                                     // move, ray.py:343-346, 380-440
+        const int dr = (a == 2) - (a == 0), dc = (a == 1) - (a == 3);            // ray.py:130-131
+        const int nr = min(max(r + dr, 0), H - 1), nc = min(max(c + dc, 0), W - 1);   // coordinates.py:22-25
+        const int ncell = nr * W + nc;
+        int here = g[cell];
+        const int T = g[ncell];
+        int ih = 0, ihn = 0;
+        if (h != 0) { ih = ig[cell]; ihn = ig[ncell]; }
+        int old = EMPTY;  // EMPTY == "None": matches no predicate below (ray.py:655 uses 100)
+        bool moved = ncell != cell;                                              // ray.py:395-396
+        const bool blocked = ((T == ROCK) & (h != HAMMER)) | ((T == TREE) & (h != AXE));   // ray.py:401-405
+        moved = moved & !blocked;
+        if (moved) {
+            r = nr; c = nc; old = T; ih = ihn;                                   // ray.py:407-411
+            int nv = T;
+            if (T == ROCK || T == BREAD) nv = EMPTY;                             // ray.py:423-425
+            else if (T == TREE) nv = STICKS;                                     // ray.py:426-428
+            else if (T == STICKS && h == HAMMER) nv = HOUSE;                     // ray.py:429-432
+            else if (T == WHEAT && h == AXE) nv = BREAD;                         // ray.py:433-438
+            if (nv != T) { wcell = ncell; wval = nv; }
+            here = nv;
+        }
+        changed = moved;
+        // eval_task_edit: for EVERY move action, successful or not (ray.py:345-346, 646-703)
+        if (old == BREAD) ach |= 1u << T_EAT_BREAD;                              // ray.py:657-659
+        else if (old == ROCK) ach |= 1u << T_CHOP_ROCK;                          // ray.py:660-662
+        else if (old == TREE) ach |= 1u << T_CHOP_TREE;                          // ray.py:663-665
+        ach = setbit(ach, T_GO_TO_HOUSE, here == HOUSE);                         // ray.py:668 (level triggered)
+        if (h == STICKS) {                                                       // ray.py:672-684
+            const bool home = (ih == STICKS) | ((ih == TREE) & ((ach >> T_CHOP_TREE) & 1u));
+            ach = setbit(ach, T_MOVE_STICKS, !home);
+        } else if (h == AXE) {                                                   // ray.py:685-693
+            if (old == WHEAT) ach |= 1u << T_MAKE_BREAD;
+            ach = setbit(ach, T_MOVE_AXE, ih != AXE);
+        } else if (h == HAMMER) {                                                // ray.py:694-702
+            if (old == STICKS) ach |= 1u << T_BUILD_HOUSE;
+            ach = setbit(ach, T_MOVE_HAMMER, ih != HAMMER);
+        }
+    }
+    if (wcell >= 0) g[wcell] = (uint8_t)wval;
+    int reward = -1;                                                             // ray.py:362-363
+    if (changed) {                                                               // ray.py:348, 361
+        const bool success = cfg.subset_reward ? ((des & ~ach) == 0)             // ray.py:763-767
+                                               : (ach == des);                   // ray.py:747-761
+        if (success) reward = M;
+    }
+    done = (t >= M) | (reward == M);                                             // ray.py:367
+    agent = (uint32_t)r | ((uint32_t)c << 8) | ((uint32_t)h << 16);
+    goal = ach | (des << 16);
+    return reward;
+}
+
+// episode statistics of a finished episode (host reduces them across ranks with one small all-reduce)
+__device__ __forceinline__ void stats_add(const CwConfig& cfg, unsigned long long* stats, uint32_t goal, int t, int reward) {
+    const bool success = reward == cfg.max_steps;
+    const long long ret = success ? (long long)cfg.max_steps - (t - 1) : -(long long)t;
+    atomicAdd(stats + 0, 1ull);
+    if (success) atomicAdd(stats + 1, 1ull);
+    atomicAdd(stats + 2, (unsigned long long)ret);
+    atomicAdd(stats + 3, (unsigned long long)t);
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        if ((goal >> i) & 1u) atomicAdd(stats + 4 + i, 1ull);
+        if ((goal >> (16 + i)) & 1u) atomicAdd(stats + 13 + i, 1ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// reset(): ray.py:156-218, executed by one full warp for world `n`.
+// Draw order (spec: oracle/compact.py reset_env): task count, task subset (169-174), placement (605-613).
+// Writes grid + init_grid (global; and `sg` if non-null, a shared copy) and episode[n]; returns agent/goal.
+// `rng` is left positioned after the placement draws so imagine_warp can continue the same stream.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& st, int64_t n, uint8_t* sg, WarpPhilox& rng,
+                                           uint32_t& agent_out, uint32_t& goal_out) {
+    const int lane = lane_id();
+    const uint32_t ep = st.episode[n];
+    rng.init(st.seed, st.env_id_base + (uint64_t)n, ep);
+    // desired_goal_vector: n_tasks = U{1..number_of_tasks} if stacking else 1; partial Fisher-Yates over
+    // selected_tasks, kept as 4-bit entries of one 64-bit word (ray.py:169-174)
+    const int ntask = cfg.stacking ? (int)rng.uniform((uint32_t)cfg.number_of_tasks) + 1 : 1;
+    uint64_t perm = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) perm |= (uint64_t)(cfg.selected[i] & 15) << (4 * i);
+    uint32_t des = 0;
+    for (int i = 0; i < ntask; i++) {
+        const int j = i + (int)rng.uniform((uint32_t)(cfg.n_selected - i));
+        const uint64_t vi = (perm >> (4 * i)) & 15, vj = (perm >> (4 * j)) & 15;
+        perm = (perm & ~((uint64_t)15 << (4 * i)) & ~((uint64_t)15 << (4 * j))) | (vj << (4 * i)) | (vi << (4 * j));
+        des |= 1u << (uint32_t)vj;
+    }
+    const int nchunk = cfg.cell_stride >> 4;
+    uint4* gg = reinterpret_cast<uint4*>(st.grid + n * cfg.cell_stride);
+    uint4* gi = reinterpret_cast<uint4*>(st.init_grid + n * cfg.cell_stride);
+    uint32_t agent_new;
+    if (st.n_fixed > 0) {
+        // generate_fixed_initial_state: uniform pick from the pre-sampled pool (ray.py:636-644)
+        const uint32_t idx = rng.uniform((uint32_t)st.n_fixed);
+        const uint4* src = reinterpret_cast<const uint4*>(st.fixed_grid + (size_t)idx * cfg.cell_stride);
+        for (int ch = lane; ch < nchunk; ch += 32) {
+            const uint4 v4 = src[ch];
+            gg[ch] = v4;
+            gi[ch] = v4;
+            if (sg) reinterpret_cast<uint4*>(sg)[ch] = v4;
+        }
+        agent_new = st.fixed_agent[idx] & 0xFFFFu;
+    } else {
+        // sample_state: 8 objects + agent on 9 distinct uniform cells (ray.py:605-613)
+        const uint32_t ncell = (uint32_t)(cfg.H * cfg.W);
+        uint32_t cells[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            uint32_t cell;
+            bool dup;
+            do {
+                cell = rng.uniform(ncell);
+                dup = false;
+#pragma unroll
+                for (int q = 0; q < k; q++) dup |= cells[q] == cell;
+            } while (dup);
+            cells[k] = cell;
+        }
+        // grid rows as 16-byte chunks, composed in registers (one chunk per lane per iteration)
+        for (int ch = lane; ch < nchunk; ch += 32) {
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if ((int)(cells[k] >> 4) == ch) {
+                    const uint32_t v = (uint32_t)(k + 1) << (8 * (cells[k] & 3));
+                    const int wi = (cells[k] >> 2) & 3;
+                    w0 |= wi == 0 ? v : 0; w1 |= wi == 1 ? v : 0; w2 |= wi == 2 ? v : 0; w3 |= wi == 3 ? v : 0;
+                }
+            }
+            const uint4 v4 = make_uint4(w0, w1, w2, w3);
+            gg[ch] = v4;
+            gi[ch] = v4;                                                         // INIT_OBS_VECTOR, ray.py:183
+            if (sg) reinterpret_cast<uint4*>(sg)[ch] = v4;
+        }
+        const uint32_t ar = cells[8] / (uint32_t)cfg.W;
+        agent_new = ar | ((cells[8] - ar * (uint32_t)cfg.W) << 8);
+    }
+    if (lane == 0) st.episode[n] = ep + 1;
+    agent_out = agent_new;                                                       // holding nothing
+    goal_out = des << 16;                                                        // achieved = 0, ray.py:176
+    __syncwarp();
+}
+
+// warp-cooperative scans over a shared-memory grid, in np.where (row-major) order
+__device__ __forceinline__ int warp_count(const uint8_t* g, int n, int code, int skip) {
+    int cnt = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        const bool p = (i < n) && (g[i] == code) && (i != skip);
+        cnt += __popc(__ballot_sync(0xffffffffu, p));
+    }
+    return cnt;
+}
+__device__ __forceinline__ int warp_nth(const uint8_t* g, int n, int code, int k, int skip) {
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        const bool p = (i < n) && (g[i] == code) && (i != skip);
+        const uint32_t m = __ballot_sync(0xffffffffu, p);
+        const int c = __popc(m);
+        if (k < c) return base + (int)__fns(m, 0, k + 1);
+        k -= c;
+    }
+    return -1;
+}
+__device__ __forceinline__ void warp_set(uint8_t* g, int cell, int code) {
+    __syncwarp();
+    if (lane_id() == 0) g[cell] = (uint8_t)code;
+    __syncwarp();
+}
+
+// imagine_obs: ray.py:220-299, by one full warp on a shared-memory scratch copy `g` of the initial grid.
+// Skills are applied in the reference's fixed order; a skill with no candidate object is skipped (the reference
+// would raise on randint(0); unreachable from sample_state worlds).
+__device__ __forceinline__ void imagine_warp(const CwConfig& cfg, uint8_t* g, uint32_t& agent, uint32_t des, WarpPhilox& rng) {
+    const int n = cfg.H * cfg.W, W = cfg.W;
+    int r = agent & 0xFF, c = (agent >> 8) & 0xFF;
+    const int acell = r * W + c;
+    int cnt, k, src, dst, fr;
+    if ((des >> T_MAKE_BREAD) & 1u) {                                            // ray.py:226-231
+        src = warp_nth(g, n, WHEAT, 0, -1);
+        if (src >= 0) warp_set(g, src, BREAD);
+    }
+    if ((des >> T_EAT_BREAD) & 1u) {                                             // ray.py:232-237
+        cnt = warp_count(g, n, BREAD, -1);
+        if (cnt) { k = (int)rng.uniform((uint32_t)cnt); warp_set(g, warp_nth(g, n, BREAD, k, -1), EMPTY); }
+    }
+    if ((des >> T_CHOP_TREE) & 1u) {                                             // ray.py:238-243
+        src = warp_nth(g, n, TREE, 0, -1);
+        if (src >= 0) warp_set(g, src, STICKS);
+    }
+    if ((des >> T_MOVE_STICKS) & 1u) {                                           // ray.py:244-257
+        cnt = warp_count(g, n, STICKS, -1);
+        if (cnt) {
+            k = (int)rng.uniform((uint32_t)cnt);
+            fr = warp_count(g, n, EMPTY, acell);                                 // [:9] -> agent cell is occupied
+            if (fr) {
+                const int spot = (int)rng.uniform((uint32_t)fr);
+                src = warp_nth(g, n, STICKS, k, -1);
+                dst = warp_nth(g, n, EMPTY, spot, acell);
+                warp_set(g, src, EMPTY);
+                warp_set(g, dst, STICKS);
+            }
+        }
+    }
+    if ((des >> T_BUILD_HOUSE) & 1u) {                                           // ray.py:258-264
+        cnt = warp_count(g, n, STICKS, -1);
+        if (cnt) { k = (int)rng.uniform((uint32_t)cnt); warp_set(g, warp_nth(g, n, STICKS, k, -1), HOUSE); }
+    }
+    if ((des >> T_CHOP_ROCK) & 1u) {                                             // ray.py:265-268
+        src = warp_nth(g, n, ROCK, 0, -1);
+        if (src >= 0) warp_set(g, src, EMPTY);
+    }
+    if ((des >> T_GO_TO_HOUSE) & 1u) {                                           // ray.py:269-276
+        cnt = warp_count(g, n, HOUSE, -1);
+        if (cnt) {
+            k = (int)rng.uniform((uint32_t)cnt);
+            dst = warp_nth(g, n, HOUSE, k, -1);
+            r = dst / W; c = dst - r * W;
+        }
+    }
+    if ((des >> T_MOVE_AXE) & 1u) {                                              // ray.py:277-286
+        src = warp_nth(g, n, AXE, 0, -1);
+        if (src >= 0) {
+            fr = warp_count(g, n, EMPTY, -1);                                    // [:8] -> agent cell allowed
+            if (fr) {
+                const int spot = (int)rng.uniform((uint32_t)fr);
+                dst = warp_nth(g, n, EMPTY, spot, -1);
+                warp_set(g, src, EMPTY);
+                warp_set(g, dst, AXE);
+            }
+        }
+    }
+    if ((des >> T_MOVE_HAMMER) & 1u) {                                           // ray.py:287-297
+        src = warp_nth(g, n, HAMMER, 0, -1);
+        if (src >= 0) {
+            fr = warp_count(g, n, EMPTY, -1);
+            if (fr) {
+                const int spot = (int)rng.uniform((uint32_t)fr);
+                dst = warp_nth(g, n, EMPTY, spot, -1);
+                warp_set(g, src, EMPTY);
+                warp_set(g, dst, HAMMER);
+            }
+        }
+    }
+    agent = (agent & 0xFFFF0000u) | (uint32_t)r | ((uint32_t)c << 8);
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// render(state): ray.py:442-486.  Expands `nbands` cell rows starting at `band0` of the shared-memory grid `sg`
+// into the shared-memory frame chunk `frame` (uint32 words; a pixel row is 3*W words = 12 bytes per cell).
+// A thread owns one cell: colour LUT -> the three 32-bit words of its 4-pixel RGB span -> 4 pixel rows; the
+// owner of the agent cell patches rows 1,2 itself (2x2 white block :483, bottom row = held colour :484-486),
+// so no second pass / barrier is needed.  Lanes hit consecutive cells => word stride 3 => conflict-free STS.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void compose_bands(const CwConfig& cfg, const uint8_t* __restrict__ sg, uint32_t agent,
+                                              int band0, int nbands, uint32_t* __restrict__ frame,
+                                              const uint32_t* __restrict__ slut, uint32_t w_magic) {
+    const int W = cfg.W, roww = 3 * W;
+    const int ar = agent & 0xFF, ac = (agent >> 8) & 0xFF, ah = (agent >> 16) & 0xFF;
+    const int acell = ar * W + ac - band0 * W;
+    const uint32_t hc = ah ? slut[ah] : 0x00FFFFFFu;
+    const int ncells = nbands * W;
+    const uint8_t* src = sg + band0 * W;
+    for (int i = threadIdx.x; i < ncells; i += blockDim.x) {
+        const int b = (int)__umulhi((uint32_t)i, w_magic);   // i / W
+        const int col = i - b * W;
+        const uint32_t rgb = slut[src[i]];
+        const uint32_t w0 = __byte_perm(rgb, 0, 0x0210), w1 = __byte_perm(rgb, 0, 0x1021), w2 = __byte_perm(rgb, 0, 0x2102);
+        uint32_t* p = frame + b * (4 * roww) + 3 * col;
+        const bool isa = i == acell;
+        p[0] = w0; p[1] = w1; p[2] = w2;
+        p[roww + 0] = isa ? (w0 | 0xFF000000u) : w0;
+        p[roww + 1] = isa ? 0xFFFFFFFFu : w1;
+        p[roww + 2] = isa ? (w2 | 0x000000FFu) : w2;
+        p[2 * roww + 0] = isa ? __byte_perm(w0, hc, 0x4210) : w0;
+        p[2 * roww + 1] = isa ? __byte_perm(hc, 0, 0x1021) : w1;
+        p[2 * roww + 2] = isa ? __byte_perm(w2, hc, 0x3216) : w2;
+        p[3 * roww + 0] = w0; p[3 * roww + 1] = w1; p[3 * roww + 2] = w2;
+    }
+}
+
+// ---- TMA bulk store (shared::cta -> global), sm_90+ : SASS UBLKCP ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+}  // namespace cw

@@ -1,0 +1,448 @@
+"""Batched CraftingWorld env: the host-side mirror of the reference's ``CraftingWorldEnvRay``
+(``gym_craftingworld/envs/craftingworld_ray.py``, "ray.py") for N independent worlds resident on one B200.
+
+Same constructor keywords (``ray.py:59-60``), same method names and return structure (``reset`` 156-218,
+``step`` 301-378, ``render`` 442-520, ``compute_reward`` 757-767, ``seed`` 145-147), batched over a leading
+``num_envs`` axis and returned as CUDA tensors.  All arithmetic happens in the hand-written sm_100a kernels behind
+the C ABI of ``include/cw_b200.h``; PyTorch only owns the device buffers and the stream.  There is no CPU path.
+
+Differences from the reference, all additive (DESIGN.md "Boundary"):
+  * frames are ``uint8`` (the reference returns int64 arrays whose values are all in 0..255 on this render path);
+  * ``auto_reset=True`` re-seeds a finished world inside the same launch: the returned reward/done belong to the
+    finished episode, the observation to the new one (the reference has no auto-reset, ``gen_info.rst:75-80``);
+  * reset randomness is a Philox4x32-10 counter stream keyed by (seed, GLOBAL env id, episode) instead of the
+    reference's MT19937 ``RandomState`` -- same distributions, results independent of how worlds are sharded;
+  * an out-of-range action is a no-op that still advances ``step_num`` (the reference raises IndexError,
+    ``ray.py:308``); pass ``validate_actions=True`` to get the exception (costs a device sync).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections.abc import Mapping
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import spaces
+
+OBJECTS = ['sticks', 'axe', 'hammer', 'rock', 'tree', 'bread', 'house', 'wheat']          # ray.py:21
+PICKUPABLE = ['sticks', 'axe', 'hammer']                                                  # ray.py:20
+TASK_LIST = ['MakeBread', 'EatBread', 'BuildHouse', 'ChopTree', 'ChopRock', 'GoToHouse', 'MoveAxe', 'MoveHammer',
+             'MoveSticks']                                                                # ray.py:40-41
+ACTION_NAMES = ['up', 'right', 'down', 'left', 'pickup', 'drop']                          # ray.py:130-131
+STATE_W = STATE_H = 21                                                                    # ray.py:43-44
+MAX_STEPS = 300                                                                           # ray.py:46
+COLORS_N = [(0, 0, 0), (110, 69, 39), (255, 105, 180), (100, 100, 200), (100, 100, 100), (0, 128, 0),
+            (205, 133, 63), (197, 91, 97), (240, 230, 140)]                               # ray.py:28-30
+FIXED_POOL_ID_BASE = 1 << 62      # Philox stream ids of the fixed_init_state pool (disjoint from env ids)
+
+
+def make_config(size=(STATE_W, STATE_H), max_steps=MAX_STEPS, task_list=TASK_LIST, selected_tasks=TASK_LIST,
+                number_of_tasks=None, stacking=True, reward_style=None) -> _lib.CwConfig:
+    """Validate the reference constructor arguments (``ray.py:59-83``) and pack them for the C ABI."""
+    W, H = (int(size[0]), int(size[1]))                                                    # ray.py:75
+    if W != H:
+        raise ValueError(f"size must be square: non-square sizes are broken upstream (IndexError), got {size}")
+    if not (3 <= H <= _lib.MAX_SIDE):
+        raise ValueError(f"size must be within 3..{_lib.MAX_SIDE}, got {size}")
+    if int(max_steps) < 1:
+        raise ValueError("max_steps must be >= 1")
+    task_list, selected_tasks = list(task_list), list(selected_tasks)
+    if not (9 <= len(task_list) <= 16):
+        raise ValueError("task_list must name the 9 skills (eval_task_edit writes bits 0..8, ray.py:657-702)")
+    if not (1 <= len(selected_tasks) <= 9):
+        raise ValueError("selected_tasks must hold 1..9 tasks")
+    for name in selected_tasks:
+        if name not in task_list:
+            raise ValueError(f"selected task {name!r} is not in task_list")                # ray.py:174 (.index)
+    n_tasks = len(selected_tasks) if number_of_tasks is None else int(number_of_tasks)     # ray.py:79
+    n_tasks = min(n_tasks, len(selected_tasks))                                            # ray.py:80-81
+    if n_tasks < 1:
+        raise ValueError("number_of_tasks must be >= 1")
+    cfg = _lib.CwConfig()
+    cfg.H, cfg.W, cfg.cell_stride, cfg.max_steps = H, W, _lib.cell_stride(H, W), int(max_steps)
+    cfg.subset_reward = 0 if reward_style is None else 1                                   # ray.py:71-74
+    cfg.stacking = 1 if stacking is True else 0                                            # ray.py:169 ("is True")
+    cfg.n_selected, cfg.number_of_tasks = len(selected_tasks), n_tasks
+    for i, name in enumerate(selected_tasks):
+        cfg.selected[i] = task_list.index(name)
+    return cfg
+
+
+class GoalInfo(Mapping):
+    """``info`` of ``step`` (``ray.py:376-378``): 9-vectors unpacked lazily from the packed device word."""
+    _KEYS = ("task_success", "desired_goal", "achieved_goal")
+
+    def __init__(self, env):
+        self._env = env
+
+    def __getitem__(self, k):
+        if k in ("task_success", "achieved_goal"):
+            return self._env.achieved_goal_vector
+        if k == "desired_goal":
+            return self._env.desired_goal_vector
+        if k == "achieved_mask":
+            return self._env.achieved_mask
+        if k == "desired_mask":
+            return self._env.desired_mask
+        raise KeyError(k)
+
+    def __iter__(self):
+        return iter(self._KEYS)
+
+    def __len__(self):
+        return len(self._KEYS)
+
+
+class BatchedCraftingWorldEnv:
+    """N independent CraftingWorld worlds on one GPU behind the reference's Env surface."""
+
+    metadata = {'render.modes': ['human', 'Non']}                                          # ray.py:57
+
+    def __init__(self, num_envs, size=(STATE_W, STATE_H), fixed_init_state=0, max_steps=MAX_STEPS, store_gif=False,
+                 render_save_rate=1, task_list=TASK_LIST, selected_tasks=TASK_LIST, number_of_tasks=None, stacking=True,
+                 reward_style=None, *, device=None, seed=None, auto_reset=True, obs_mode="pixels", env_id_base=0,
+                 goal_images=True, obs_buffers=1, validate_actions=False):
+        if store_gif:
+            raise NotImplementedError("GIF recording (ray.py:565-597, 769-782) is a host-side debugging side channel; "
+                                      "out of scope (DESIGN.md)")
+        if obs_mode not in ("pixels", "compact"):
+            raise ValueError("obs_mode must be 'pixels' or 'compact'")
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self.cfg = make_config(size, max_steps, task_list, selected_tasks, number_of_tasks, stacking, reward_style)
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("gym_craftingworld_b200 needs a CUDA device: there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("gym_craftingworld_b200 needs a CUDA device: there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.STATE_W, self.STATE_H = self.cfg.W, self.cfg.H
+        self.MAX_STEPS = self.cfg.max_steps
+        self.task_list, self.selected_tasks = list(task_list), list(selected_tasks)
+        self.number_of_tasks, self.stacking = self.cfg.number_of_tasks, bool(self.cfg.stacking)
+        self.fixed_init_state = int(fixed_init_state)
+        self.auto_reset, self.obs_mode = bool(auto_reset), obs_mode
+        self.goal_images = bool(goal_images) and obs_mode == "pixels"
+        self.validate_actions = bool(validate_actions)
+        self.env_id_base = int(env_id_base)
+        self.compute_reward = self.compute_reward_equal if reward_style is None else self.compute_reward_subset
+
+        N, H, W, dev = self.num_envs, self.cfg.H, self.cfg.W, self.device
+        pw, ph = 4 * W, 4 * H
+        img = spaces.Box(0, 255, (pw, ph, 3), np.uint8)
+        self.observation_space = spaces.Dict(dict(observation=img, desired_goal=img, achieved_goal=img,
+                                                  init_observation=img))                  # ray.py:85-92
+        vec = spaces.Box(0, 1, (W, H, len(OBJECTS) + 1 + len(PICKUPABLE)), np.uint8)
+        gvec = spaces.Box(0, 1, (1, len(self.task_list)), np.uint8)
+        self.observation_vector_space = spaces.Dict(dict(observation=vec, desired_goal=gvec, achieved_goal=gvec,
+                                                         init_observation=vec))           # ray.py:94-110
+        self.ACTIONS = list(ACTION_NAMES)
+        self.action_space = spaces.Discrete(len(self.ACTIONS))                             # ray.py:133
+
+        # ---- device-resident SoA state (layout: include/cw_b200.h) -----------------------------------
+        stride = self.cfg.cell_stride
+        self.grid = torch.zeros((N, stride), dtype=torch.uint8, device=dev)
+        self.init_grid = torch.zeros((N, stride), dtype=torch.uint8, device=dev)
+        self.agent = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.goal = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.t = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.episode = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.reward = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._done_u8 = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.done = self._done_u8.view(torch.bool)
+        self.stats = torch.zeros(_lib.STATS_LEN, dtype=torch.int64, device=dev)
+        self.frame_shape = (N, ph, pw, 3)
+        self._obs_ring, self._ring_pos = [], 0
+        self.obs = self.desired_goal = self.init_obs = None
+        if obs_mode == "pixels":
+            self._obs_ring = [torch.zeros(self.frame_shape, dtype=torch.uint8, device=dev) for _ in range(max(1, int(obs_buffers)))]
+            self.obs = self._obs_ring[0]
+            if self.goal_images:
+                self.desired_goal = torch.zeros(self.frame_shape, dtype=torch.uint8, device=dev)
+                self.init_obs = torch.zeros(self.frame_shape, dtype=torch.uint8, device=dev)
+        self._fixed_grid = self._fixed_agent = None
+        self._seed = None
+        self._state = _lib.CwState()
+        self.seed(seed)
+        self._info = GoalInfo(self)
+        self._bits = torch.arange(len(self.task_list), dtype=torch.int32, device=dev)
+        self._is_reset = False
+
+    # ------------------------------------------------------------------------------------------------
+    def seed(self, seed=None):
+        """``seed`` (``ray.py:145-147``): sets the Philox key; returns ``[seed]``."""
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little") >> 1
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        if self.fixed_init_state:
+            self._generate_fixed_states(self.fixed_init_state)
+        self._refresh_state_struct()
+        return [self._seed]
+
+    def _refresh_state_struct(self):
+        s = self._state
+        s.grid, s.init_grid = self.grid.data_ptr(), self.init_grid.data_ptr()
+        s.agent, s.goal, s.t, s.episode = self.agent.data_ptr(), self.goal.data_ptr(), self.t.data_ptr(), self.episode.data_ptr()
+        s.n, s.seed, s.env_id_base = self.num_envs, self._seed, self.env_id_base
+        if self._fixed_grid is not None:
+            s.fixed_grid, s.fixed_agent, s.n_fixed = self._fixed_grid.data_ptr(), self._fixed_agent.data_ptr(), self.fixed_init_state
+        else:
+            s.fixed_grid, s.fixed_agent, s.n_fixed = None, None, 0
+
+    def _generate_fixed_states(self, n):
+        """``generate_fixed_states`` (``ray.py:149-154``): pre-sample ``n`` worlds with ``sample_state``."""
+        dev, stride = self.device, self.cfg.cell_stride
+        pool = _lib.CwState()
+        g = torch.zeros((n, stride), dtype=torch.uint8, device=dev)
+        ig = torch.zeros_like(g)
+        ag, gl, t, ep = (torch.zeros(n, dtype=torch.int32, device=dev) for _ in range(4))
+        pool.grid, pool.init_grid, pool.agent, pool.goal = g.data_ptr(), ig.data_ptr(), ag.data_ptr(), gl.data_ptr()
+        pool.t, pool.episode, pool.n, pool.seed, pool.env_id_base = t.data_ptr(), ep.data_ptr(), n, self._seed, FIXED_POOL_ID_BASE
+        pool.n_fixed = 0
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cw_reset(C.byref(self.cfg), C.byref(pool), None, None, None, None, self._stream()), "cw_reset(pool)")
+        self._fixed_grid, self._fixed_agent = g, ag
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- reference-style attributes ------------------------------------------------------------------
+    @property
+    def achieved_mask(self):
+        return self.goal & 0xFFFF
+
+    @property
+    def desired_mask(self):
+        return (self.goal >> 16) & 0xFFFF
+
+    @property
+    def achieved_goal_vector(self):
+        """``uint8[N, len(task_list)]`` (the reference's ``int[1, 9]`` per world, ``ray.py:176``)."""
+        return ((self.achieved_mask.unsqueeze(1) >> self._bits) & 1).to(torch.uint8)
+
+    @property
+    def desired_goal_vector(self):
+        return ((self.desired_mask.unsqueeze(1) >> self._bits) & 1).to(torch.uint8)
+
+    @property
+    def step_num(self):
+        return self.t
+
+    @property
+    def ep_no(self):
+        return (self.episode - 1).clamp_(min=0)
+
+    @property
+    def agent_pos(self):
+        """``int32[N, 2]`` (row, col)."""
+        return torch.stack((self.agent & 0xFF, (self.agent >> 8) & 0xFF), dim=1)
+
+    @property
+    def holding(self):
+        return (self.agent >> 16) & 0xFF
+
+    @property
+    def grid_view(self):
+        """Zero-copy ``uint8[N, H, W]`` view of the object-code grid (the compact observation)."""
+        H, W = self.cfg.H, self.cfg.W
+        return self.grid[:, :H * W].view(self.num_envs, H, W)
+
+    def onehot(self, init=False):
+        """One-hot ``uint8[N, H, W, 12]`` state (``obs_one_hot`` / ``INIT_OBS_VECTOR``, ``ray.py:605-613, 183``)."""
+        out = torch.empty((self.num_envs, self.cfg.H, self.cfg.W, 12), dtype=torch.uint8, device=self.device)
+        src = self.init_grid if init else self.grid
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cw_onehot(C.byref(self.cfg), src.data_ptr(), self.agent.data_ptr(), out.data_ptr(),
+                                           self.num_envs, self._stream()), "cw_onehot")
+        return out
+
+    @property
+    def observation_vector(self):
+        """``ray.py:185-187``; note ``init_observation`` carries the CURRENT agent/holding channels (the kernels keep
+        only the object codes of INIT_OBS_VECTOR, which is all the hot path ever reads)."""
+        return {"observation": self.onehot(), "desired_goal": self.desired_goal_vector,
+                "achieved_goal": self.achieved_goal_vector, "init_observation": self.onehot(init=True)}
+
+    # ---- observations ----------------------------------------------------------------------------------
+    def _observation(self):
+        if self.obs_mode == "pixels":
+            return {"observation": self.obs, "desired_goal": self.desired_goal, "achieved_goal": self.obs,
+                    "init_observation": self.init_obs}                                      # ray.py:194-196
+        return {"observation": self.grid_view, "agent": self.agent, "desired_goal": self.desired_mask,
+                "achieved_goal": self.achieved_mask, "init_observation": self.init_grid}
+
+    @property
+    def observation(self):
+        return self._observation()
+
+    def _ptr(self, t):
+        return None if t is None else t.data_ptr()
+
+    # ---- reset / step ------------------------------------------------------------------------------------
+    def reset(self, mask=None):
+        """``reset`` (``ray.py:156-218``) for all worlds, or for ``mask`` (bool/uint8 ``[N]``) only."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if m.shape != (self.num_envs,):
+                raise ValueError(f"mask must have shape ({self.num_envs},)")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cw_reset(C.byref(self.cfg), C.byref(self._state), self._ptr(m), self._ptr(self.obs),
+                                          self._ptr(self.desired_goal), self._ptr(self.init_obs), self._stream()), "cw_reset")
+        self._is_reset = True
+        return self._observation()
+
+    def _as_actions(self, actions):
+        a = actions
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.asarray(a).reshape(-1), device=self.device)
+        if a.device != self.device:
+            a = a.to(self.device)
+        if self.validate_actions and bool(((a < 0) | (a >= len(self.ACTIONS))).any()):
+            raise IndexError("action out of range [0, 6)")                                  # ray.py:308
+        if a.dtype != torch.uint8:
+            a = a.to(torch.uint8)
+        return a.contiguous()
+
+    def step(self, actions):
+        """``step`` (``ray.py:301-378``) for all worlds: ``(obs dict, reward int32[N], done bool[N], info)``.
+        One kernel launch; asynchronous on the current stream (CUDA-graph capturable)."""
+        a = self._as_actions(actions)
+        if a.shape != (self.num_envs,):
+            raise ValueError(f"actions must have shape ({self.num_envs},), got {tuple(a.shape)}")
+        flags = _lib.F_AUTO_RESET if self.auto_reset else 0
+        with torch.cuda.device(self.device):
+            if self.obs_mode == "pixels":
+                if len(self._obs_ring) > 1:
+                    self._ring_pos = (self._ring_pos + 1) % len(self._obs_ring)
+                    self.obs = self._obs_ring[self._ring_pos]
+                rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                                              self._done_u8.data_ptr(), self.obs.data_ptr(), self._ptr(self.desired_goal),
+                                              self._ptr(self.init_obs), self.stats.data_ptr(), flags, self._stream())
+            else:
+                rc = self._lib.cw_step(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                                       self._done_u8.data_ptr(), self.stats.data_ptr(), flags, self._stream())
+        _lib.check(rc, "cw_step")
+        return self._observation(), self.reward, self.done, self._info
+
+    def rollout(self, actions, return_trace=True):
+        """K steps in ONE launch on an open-loop action tape ``uint8[K, N]`` (compact observations only).
+        Returns ``(reward int32[K,N], done bool[K,N])`` or ``None`` when ``return_trace`` is False."""
+        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions), device=self.device)
+        a = a.to(device=self.device, dtype=torch.uint8).contiguous()
+        if a.dim() != 2 or a.shape[1] != self.num_envs:
+            raise ValueError(f"actions must have shape (K, {self.num_envs})")
+        K = a.shape[0]
+        rew = dn = None
+        if return_trace:
+            rew = torch.empty((K, self.num_envs), dtype=torch.int32, device=self.device)
+            dn = torch.empty((K, self.num_envs), dtype=torch.uint8, device=self.device)
+        flags = _lib.F_AUTO_RESET if self.auto_reset else 0
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cw_rollout(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self._ptr(rew), self._ptr(dn),
+                                            self.stats.data_ptr(), K, flags, self._stream()), "cw_rollout")
+        return (rew, dn.view(torch.bool)) if return_trace else None
+
+    def render(self, state=None, mode="Non", tile_size=4):
+        """``render`` (``ray.py:442-520``).  ``state=None`` renders the current worlds; otherwise ``state`` is
+        ``(grid uint8[M,H,W], r[M], c[M], hold[M])`` and a fresh ``uint8[M,4H,4W,3]`` tensor is returned."""
+        if tile_size != 4:
+            raise ValueError("tile_size is fixed at 4 (the reference ignores the argument, ray.py:478-479)")
+        H, W = self.cfg.H, self.cfg.W
+        if state is None:
+            grid, agent, M = self.grid, self.agent, self.num_envs
+            out = self.obs if self.obs is not None else torch.empty(self.frame_shape, dtype=torch.uint8, device=self.device)
+        else:
+            g, r, c, h = state
+            g = torch.as_tensor(g, device=self.device).to(torch.uint8).reshape(-1, H * W)
+            M = g.shape[0]
+            grid = torch.zeros((M, self.cfg.cell_stride), dtype=torch.uint8, device=self.device)
+            grid[:, :H * W] = g
+            r, c, h = (torch.as_tensor(x, device=self.device).to(torch.int32).reshape(-1) for x in (r, c, h))
+            agent = (r | (c << 8) | (h << 16)).contiguous()
+            out = torch.empty((M, 4 * H, 4 * W, 3), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cw_render(C.byref(self.cfg), grid.data_ptr(), agent.data_ptr(), out.data_ptr(), M, self._stream()),
+                       "cw_render")
+        return out
+
+    # ---- reward (host-visible restatement for callers that relabel goals, e.g. HER) ------------------------
+    def _to_mask(self, g):
+        """Accept packed masks ``int[N]`` or bit vectors ``[..., len(task_list)]`` (a lone 0/1 vector of that length
+        is read as bits, like the reference's ``achieved_goal_vector[0]``)."""
+        g = torch.as_tensor(g, device=self.device)
+        nb = len(self.task_list)
+        is_bits = (g.dim() >= 2 and g.shape[-1] == nb) or (g.dim() == 1 and g.numel() == nb and int(g.max()) <= 1)
+        if is_bits:
+            return (g.reshape(-1, nb).to(torch.int32) << self._bits).sum(dim=1).to(torch.int32)
+        return g.to(torch.int32).reshape(-1)
+
+    def compute_reward_equal(self, achieved_goal=None, desired_goal=None, info=None):
+        """``compute_reward_equal`` (``ray.py:757-761``): MAX_STEPS where achieved == desired else -1."""
+        a, d = self._to_mask(achieved_goal), self._to_mask(desired_goal)
+        return torch.where(a == d, self.MAX_STEPS, -1).to(torch.int32)
+
+    def compute_reward_subset(self, achieved_goal=None, desired_goal=None, info=None):
+        """``compute_reward_subset`` (``ray.py:763-767``): MAX_STEPS where desired is a subset of achieved."""
+        a, d = self._to_mask(achieved_goal), self._to_mask(desired_goal)
+        return torch.where((d & ~a) == 0, self.MAX_STEPS, -1).to(torch.int32)
+
+    # ---- state injection / extraction (parity tests upload reference-generated states) ---------------------
+    def load_state(self, grid, r, c, hold, desired, achieved=None, t=None, init_grid=None):
+        """Inject compact states: ``grid uint8[N,H,W]``, ``r,c,hold,desired[N]``."""
+        N, H, W, dev = self.num_envs, self.cfg.H, self.cfg.W, self.device
+
+        def vec(x, dtype=torch.int32):
+            return torch.as_tensor(np.asarray(x), device=dev).to(dtype).reshape(N)
+
+        g = torch.as_tensor(np.asarray(grid), device=dev).to(torch.uint8).reshape(N, H * W)
+        self.grid.zero_()
+        self.grid[:, :H * W] = g
+        if init_grid is None:
+            self.init_grid.copy_(self.grid)
+        else:
+            self.init_grid.zero_()
+            self.init_grid[:, :H * W] = torch.as_tensor(np.asarray(init_grid), device=dev).to(torch.uint8).reshape(N, H * W)
+        self.agent.copy_(vec(r) | (vec(c) << 8) | (vec(hold) << 16))
+        ach = torch.zeros(N, dtype=torch.int32, device=dev) if achieved is None else vec(achieved)
+        self.goal.copy_(ach | (vec(desired) << 16))
+        if t is None:
+            self.t.zero_()
+        else:
+            self.t.copy_(vec(t))
+        if self.obs_mode == "pixels":
+            self.render()
+            if self.goal_images:
+                self.init_obs.copy_(self.obs)
+                with torch.cuda.device(self.device):
+                    _lib.check(self._lib.cw_imagine(C.byref(self.cfg), C.byref(self._state), self.desired_goal.data_ptr(),
+                                                    self._stream()), "cw_imagine")
+        self._is_reset = True
+        return self._observation()
+
+    def export_state(self):
+        """Compact state as NumPy arrays (Appendix B.3)."""
+        H, W = self.cfg.H, self.cfg.W
+        ag, gl = self.agent.cpu().numpy().astype(np.uint32), self.goal.cpu().numpy().astype(np.uint32)
+        return {"grid": self.grid[:, :H * W].reshape(-1, H, W).cpu().numpy(),
+                "init_grid": self.init_grid[:, :H * W].reshape(-1, H, W).cpu().numpy(),
+                "r": (ag & 0xFF).astype(np.uint8), "c": ((ag >> 8) & 0xFF).astype(np.uint8),
+                "hold": ((ag >> 16) & 0xFF).astype(np.uint8), "achieved": (gl & 0xFFFF).astype(np.uint16),
+                "desired": (gl >> 16).astype(np.uint16), "t": self.t.cpu().numpy(), "episode": self.episode.cpu().numpy()}
+
+    # ---- statistics ------------------------------------------------------------------------------------------
+    def episode_stats(self, stats=None):
+        """Finished-episode statistics accumulated on the device (this rank's worlds unless ``stats`` is given)."""
+        s = (self.stats if stats is None else stats).cpu().numpy()
+        n = max(int(s[0]), 1)
+        return {"episodes": int(s[0]), "successes": int(s[1]), "success_rate": s[1] / n, "mean_return": s[2] / n,
+                "mean_length": s[3] / n, "achieved_counts": s[4:13].tolist(), "desired_counts": s[13:22].tolist()}
+
+    def close(self):
+        pass

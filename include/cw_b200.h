@@ -1,0 +1,145 @@
+/* cw_b200.h -- C ABI of the B200-native batched CraftingWorld hot path (libcw_b200.so).
+ *
+ * The reference (lauradarcy/gym-craftingworld) is pure Python and has no FFI of its own; its boundary is the Gym
+ * Env protocol of CraftingWorldEnvRay (gym_craftingworld/envs/craftingworld_ray.py, "ray.py" below).  Each entry
+ * point here replaces the per-env Python method(s) cited beside it, for N independent worlds per call.  Host side:
+ * gym_craftingworld_b200/env.py (same method names / argument meaning as the reference class) binds these with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `uint8_t* / uint32_t* / int32_t* / int64_t*` below that is not marked
+ *     "host" is a DEVICE pointer owned by the caller (PyTorch in our host layer); the library never allocates,
+ *     frees or retains them (the cw_host_* family is the exception: it owns its own device + pinned buffers).
+ *   - `stream` is a cudaStream_t passed as void*; all device entry points are asynchronous on it and never
+ *     synchronise the host.
+ *   - return value: 0 on success, a positive cudaError_t, or a negative CW_E_* argument error. Never throws.
+ *   - out-of-range actions (>5) are a defined no-op that still advances step_num (the reference raises
+ *     IndexError, ray.py:308); the Python layer can validate in debug mode.
+ *
+ * Device state (SoA, all integer), N = state->n worlds:
+ *   grid, init_grid  uint8 [N][cell_stride]  cell = row*W + col, cell_stride = roundup(H*W,16);
+ *                                            code 0 empty, k+1 = OBJECTS[k] (ray.py:21): 1 sticks 2 axe 3 hammer
+ *                                            4 rock 5 tree 6 bread 7 house 8 wheat.  init_grid = INIT_OBS_VECTOR
+ *                                            object codes (ray.py:183), only read by the Move* predicates.
+ *   agent            uint32[N]               row | col<<8 | hold<<16   hold: 0 none 1 sticks 2 axe 3 hammer
+ *   goal             uint32[N]               achieved | desired<<16    bit i = TASK_LIST[i] (ray.py:40-41)
+ *   t                int32 [N]               step_num (ray.py:203, 309)
+ *   episode          uint32[N]               resets performed so far = Philox counter word of the next reset
+ *   obs, goal_obs    uint8 [N][4H][4W][3]    RGB frames (ray.py:442-486); goal_obs = imagine_obs (ray.py:220-299)
+ *   stats            int64 [CW_STATS_LEN]    0 episodes 1 successes 2 return_sum 3 length_sum
+ *                                            4..12 achieved-skill counts 13..21 desired-skill counts (finished eps)
+ */
+#ifndef CW_B200_H
+#define CW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CW_ABI_VERSION 1
+#define CW_STATS_LEN 24
+#define CW_MAX_SIDE 64 /* H, W <= 64 (cell_stride <= 4096) */
+
+/* argument errors */
+#define CW_E_BADCONFIG (-1)
+#define CW_E_NULLPTR (-2)
+#define CW_E_BADFLAGS (-3)
+#define CW_E_BADHANDLE (-4)
+
+/* flags */
+#define CW_F_AUTO_RESET 1 /* on done: add the episode to stats, Philox-reset the world in the same launch; the
+                             returned reward/done are the finished episode's, state/obs the new episode's */
+
+/* Constructor arguments of the reference that reach the hot path (ray.py:59-83). */
+typedef struct CwConfig {
+    int32_t H, W;            /* size; square upstream (non-square is broken there) */
+    int32_t cell_stride;     /* roundup(H*W, 16) */
+    int32_t max_steps;       /* MAX_STEPS, also the success reward (ray.py:46, 759) */
+    int32_t subset_reward;   /* reward_style is not None -> compute_reward_subset (ray.py:71-74, 763-767) */
+    int32_t stacking;        /* ray.py:83, 169 */
+    int32_t n_selected;      /* len(selected_tasks) in 1..9 */
+    int32_t number_of_tasks; /* ray.py:79-81, in 1..n_selected */
+    uint8_t selected[16];    /* task bit of each selected task: task_list.index(selected_tasks[i]) (ray.py:174) */
+} CwConfig;
+
+typedef struct CwState {
+    uint8_t* grid;
+    uint8_t* init_grid;
+    uint32_t* agent;
+    uint32_t* goal;
+    int32_t* t;
+    uint32_t* episode;
+    int64_t n;            /* worlds in this slice */
+    uint64_t seed;        /* Philox key */
+    uint64_t env_id_base; /* global id of world 0 of this slice: streams are keyed by GLOBAL id, so results do
+                             not depend on how worlds are sharded over ranks */
+    /* fixed_init_state pool (ray.py:116-118, 149-154, 630-644): when n_fixed > 0 a reset draws
+     * uniform(n_fixed) and copies that pre-sampled world instead of sampling a new placement */
+    const uint8_t* fixed_grid;   /* uint8 [n_fixed][cell_stride], nullable */
+    const uint32_t* fixed_agent; /* uint32[n_fixed] */
+    int64_t n_fixed;
+} CwState;
+
+int cw_abi_version(void);
+const char* cw_error_string(int code);
+
+/* reset(): ray.py:156-218 -- task sampling (169-174), sample_state (599-628), INIT copy (183), counters (203);
+ * goal_obs (nullable) receives imagine_obs (220-299), obs (nullable) the first frame (192) and init_obs
+ * (nullable, needs obs) a second copy of it (INIT_OBS, 193).
+ * mask (nullable, device uint8[N]): reset only worlds with mask[n] != 0; others are untouched (and not rendered).
+ * RNG: Philox4x32-10, key = seed, counter = (global env id, episode[n], block); episode[n] += 1. */
+int cw_reset(const CwConfig* cfg, const CwState* st, const uint8_t* mask, uint8_t* obs, uint8_t* goal_obs,
+             uint8_t* init_obs, void* stream);
+
+/* step(action) without pixels: ray.py:301-378 (pickup 314-327, drop 329-341, __move_agent 380-440 with the Coord
+ * clamp coordinates.py:22-35, eval_task_edit 646-703, compute_reward_equal/_subset 747-767, done 367).
+ * One thread per world.  reward int32[N] (-1 or max_steps), done uint8[N]; stats nullable. */
+int cw_step(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
+            int64_t* stats, int flags, void* stream);
+
+/* render(state): ray.py:442-486 (== the incremental render_edit 522-557 on every reachable state). */
+int cw_render(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, uint8_t* obs, int64_t n,
+              void* stream);
+
+/* step + (auto-reset) + render fused in one launch: what one reference `obs, r, d, info = env.step(a)` does
+ * (ray.py:301-378 incl. render_edit 358), for N worlds.  goal_obs / init_obs (nullable) are rewritten only for
+ * worlds that auto-reset in this call (desired_goal and init_observation of the new episode, ray.py:191-196). */
+int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
+                   uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, void* stream);
+
+/* K consecutive steps in one launch (open-loop action tape actions[K][N]); reward/done [K][N] nullable.
+ * Same per-step semantics as cw_step. */
+int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
+               int64_t* stats, int K, int flags, void* stream);
+
+/* imagine_obs on the CURRENT state (ray.py:220-299) without resetting: goal image of each world using the stream
+ * (seed, global id, episode[n]).  For states injected with load_state. */
+int cw_imagine(const CwConfig* cfg, const CwState* st, uint8_t* goal_obs, void* stream);
+
+/* One-hot observation_vector (ray.py:94-98, 605-613; the obs of CraftingWorldEnvOneHot): uint8[N][H][W][12],
+ * channels 0..7 objects, 8 agent, 9..11 holding sticks/axe/hammer (at the agent cell). */
+int cw_onehot(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, uint8_t* onehot, int64_t n,
+              void* stream);
+
+/* ---- host-buffer API: the env behind an opaque handle, all arguments HOST pointers ----------------------
+ * The drop-in for a host-language caller without device memory of its own: the library owns the device state,
+ * pinned staging buffers and streams; each call copies actions host->device, runs the fused launch(es) in
+ * slices, and copies reward/done (and obs if non-NULL) device->host, overlapping copies with compute.
+ * Calls on one handle are not re-entrant (like the reference env object). */
+typedef struct CwHostEnv CwHostEnv;
+int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, uint64_t env_id_base, int flags,
+                   CwHostEnv** out);
+int cw_host_reset(CwHostEnv* env, uint8_t* obs_host /*nullable*/, uint8_t* goal_obs_host /*nullable*/);
+int cw_host_step(CwHostEnv* env, const uint8_t* actions_host, int32_t* reward_host, uint8_t* done_host,
+                 uint8_t* obs_host /*nullable: pixels stay on the device*/);
+int cw_host_stats(CwHostEnv* env, int64_t* stats_host /*[CW_STATS_LEN]*/);
+/* device pointers of the handle's state, for callers that DO have a device-side consumer (e.g. a policy) */
+int cw_host_device_state(CwHostEnv* env, CwState* out_state, uint8_t** out_obs);
+int cw_host_destroy(CwHostEnv* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CW_B200_H */

@@ -208,6 +208,10 @@ static void imagine_one(const CwoConfig *cfg, uint8_t *g, uint32_t *agent, uint3
     *agent = (*agent & 0xFFFF0000u) | (uint32_t)r | ((uint32_t)c << 8);
 }
 
+/* fixed_init_state pool (ray.py:116-118, 149-154): set once by the test, read by every reset */
+static const uint8_t *g_fixed_grid = NULL; static const uint32_t *g_fixed_agent = NULL; static int64_t g_fixed_n = 0;
+void cwo_set_fixed_pool(const uint8_t *grid, const uint32_t *agent, int64_t n) { g_fixed_grid = grid; g_fixed_agent = agent; g_fixed_n = n; }
+
 /* reset(): ray.py:156-218 on the Philox stream (draw order: task count, task subset, placement, imagine) */
 static void reset_one(const CwoConfig *cfg, uint8_t *g, uint8_t *ig, uint32_t *agent, uint32_t *goal, int32_t *t,
                       uint32_t *episode, uint64_t seed, uint64_t env_id, uint8_t *goal_obs) {
@@ -222,17 +226,24 @@ static void reset_one(const CwoConfig *cfg, uint8_t *g, uint8_t *ig, uint32_t *a
         uint8_t tmp = sel[i]; sel[i] = sel[j]; sel[j] = tmp;
         des |= 1u << sel[i];
     }
-    /* sample_state, ray.py:605-613 */
-    int cells[9];
-    for (int k = 0; k < 9; k++) {
-        int cell, dup;
-        do { cell = (int)uniform(&s, cfg->H * cfg->W); dup = 0; for (int q = 0; q < k; q++) dup |= cells[q] == cell; } while (dup);
-        cells[k] = cell;
+    if (g_fixed_n > 0) {
+        /* generate_fixed_initial_state, ray.py:630-644: uniform pick from the pre-sampled pool */
+        uint32_t idx = uniform(&s, (uint32_t)g_fixed_n);
+        memcpy(g, g_fixed_grid + (size_t)idx * cfg->cell_stride, cfg->cell_stride);
+        *agent = g_fixed_agent[idx] & 0xFFFFu;
+    } else {
+        /* sample_state, ray.py:605-613 */
+        int cells[9];
+        for (int k = 0; k < 9; k++) {
+            int cell, dup;
+            do { cell = (int)uniform(&s, cfg->H * cfg->W); dup = 0; for (int q = 0; q < k; q++) dup |= cells[q] == cell; } while (dup);
+            cells[k] = cell;
+        }
+        memset(g, 0, cfg->cell_stride);
+        for (int k = 0; k < 8; k++) g[cells[k]] = (uint8_t)(k + 1);
+        *agent = (uint32_t)(cells[8] / cfg->W) | ((uint32_t)(cells[8] % cfg->W) << 8);
     }
-    memset(g, 0, cfg->cell_stride);
-    for (int k = 0; k < 8; k++) g[cells[k]] = (uint8_t)(k + 1);
     memcpy(ig, g, cfg->cell_stride);                                             /* ray.py:183 */
-    *agent = (uint32_t)(cells[8] / cfg->W) | ((uint32_t)(cells[8] % cfg->W) << 8);
     *goal = des << 16;                                                           /* ray.py:176 */
     *t = 0;                                                                      /* ray.py:203 */
     if (goal_obs) {                                                              /* ray.py:191 */

@@ -150,6 +150,17 @@ class OracleBatch:
                                  C.c_int64(self.N), C.c_int(K), C.c_int(nthreads))
 
 
+def set_fixed_pool(grid=None, agent=None):
+    """Install (or clear, with None) the fixed_init_state pool used by every subsequent reset.  The arrays must stay
+    alive while installed."""
+    lib = load()
+    if grid is None:
+        lib.cwo_set_fixed_pool(None, None, C.c_int64(0))
+    else:
+        assert grid.dtype == np.uint8 and agent.dtype == np.uint32 and grid.flags.c_contiguous
+        lib.cwo_set_fixed_pool(_p(grid), _p(agent), C.c_int64(grid.shape[0]))
+
+
 def philox(ctr, key):
     lib = load()
     c = (C.c_uint32 * 4)(*ctr)

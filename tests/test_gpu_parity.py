@@ -1,0 +1,349 @@
+"""GPU (-m gpu): the CUDA path, called through the Python facade and hence the C ABI, against
+(i) the frozen reference traces in tests/golden and (ii) the C oracle on the same seeded inputs.  Bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import native, ref_shim
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cw():
+    import gym_craftingworld_b200 as pkg
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return pkg
+
+
+def make_env(cw, d, **kw):
+    B = d["actions"].shape[0]
+    kw.setdefault("auto_reset", False)
+    kw.setdefault("goal_images", False)
+    env = cw.BatchedCraftingWorldEnv(B, size=(d["W"], d["H"]), max_steps=d["max_steps"],
+                                     reward_style=("subset" if d["subset"] else None), seed=0, **kw)
+    env.load_state(d["grid0"], d["r0"], d["c0"], d["hold0"], d["desired"])
+    return env
+
+
+def assert_state_equals_golden(env, d, t, where):
+    s = env.export_state()
+    assert np.array_equal(s["grid"], d["grid"][:, t]), where
+    assert np.array_equal(s["r"], d["r"][:, t]) and np.array_equal(s["c"], d["c"][:, t]), where
+    assert np.array_equal(s["hold"], d["hold"][:, t]), where
+    assert np.array_equal(s["achieved"], d["achieved"][:, t]), where
+
+
+@pytest.mark.parametrize("name", gu.golden_files())
+def test_fused_step_render_matches_reference_trace(cw, name):
+    """cw_step_render (one fused launch per step) reproduces the reference trace: state, reward, done, pixels."""
+    d = gu.load(name)
+    env = make_env(cw, d)
+    B, T = d["actions"].shape
+    fidx = {int(t): i for i, t in enumerate(d["frame_t"])}
+    assert np.array_equal(env.obs.cpu().numpy(), d["frame0"])
+    for t in range(T):
+        obs, reward, done, info = env.step(torch.from_numpy(d["actions"][:, t]).cuda())
+        where = f"{name} step {t}"
+        assert np.array_equal(reward.cpu().numpy(), d["reward"][:, t]), where
+        assert np.array_equal(done.cpu().numpy(), d["done"][:, t].astype(bool)), where
+        assert_state_equals_golden(env, d, t, where)
+        frames = obs["observation"].cpu().numpy()
+        assert [gu.crc(f) for f in frames] == list(d["frame_crc"][:, t]), where
+        if t in fidx:
+            assert np.array_equal(frames, d["frames"][:, fidx[t]]), where
+    assert np.array_equal(info["achieved_goal"].cpu().numpy(),
+                          (d["achieved"][:, -1, None] >> np.arange(9)) & 1)
+
+
+@pytest.mark.parametrize("name", ["quirks_5x5.npz", "quirks_5x5_subset.npz", "dense_8x8.npz", "dense_21x21.npz", "dense_32x32.npz"])
+def test_compact_step_then_render_matches_reference_trace(cw, name):
+    """cw_step (thread-per-world kernel) + cw_render as separate launches give the same trace."""
+    d = gu.load(name)
+    env = make_env(cw, d, obs_mode="compact")
+    B, T = d["actions"].shape
+    for t in range(T):
+        obs, reward, done, _ = env.step(d["actions"][:, t])
+        where = f"{name} step {t}"
+        assert np.array_equal(reward.cpu().numpy(), d["reward"][:, t]), where
+        assert np.array_equal(done.cpu().numpy(), d["done"][:, t].astype(bool)), where
+        assert_state_equals_golden(env, d, t, where)
+        assert np.array_equal(obs["observation"].cpu().numpy(), d["grid"][:, t]), where
+        if t % 16 == 0 or t == T - 1:
+            frames = env.render().cpu().numpy()
+            assert [gu.crc(f) for f in frames] == list(d["frame_crc"][:, t]), where
+
+
+@pytest.mark.parametrize("name", ["dense_5x5_subset.npz", "dense_21x21.npz", "sampled_21x21.npz"])
+def test_rollout_matches_reference_trace(cw, name):
+    """cw_rollout: the whole T-step action tape in ONE launch reproduces every per-step reward/done and the final state."""
+    d = gu.load(name)
+    env = make_env(cw, d, obs_mode="compact")
+    T = d["actions"].shape[1]
+    rew, dn = env.rollout(np.ascontiguousarray(d["actions"].T))
+    assert np.array_equal(rew.cpu().numpy(), d["reward"].T)
+    assert np.array_equal(dn.cpu().numpy(), d["done"].T.astype(bool))
+    assert_state_equals_golden(env, d, T - 1, name)
+    assert np.array_equal(env.t.cpu().numpy(), np.full(d["actions"].shape[0], T))
+
+
+def oracle_for(env, seed):
+    cfg = native.make_config(H=env.cfg.H, W=env.cfg.W, max_steps=env.cfg.max_steps, subset_reward=bool(env.cfg.subset_reward),
+                             stacking=bool(env.cfg.stacking), selected=tuple(env.cfg.selected[i] for i in range(env.cfg.n_selected)),
+                             number_of_tasks=env.cfg.number_of_tasks)
+    return native.OracleBatch(cfg, env.num_envs, seed=seed, env_id_base=env.env_id_base)
+
+
+def assert_env_equals_oracle(env, ob, where=""):
+    assert np.array_equal(env.grid.cpu().numpy(), ob.grid), where + " grid"
+    assert np.array_equal(env.init_grid.cpu().numpy(), ob.init_grid), where + " init_grid"
+    assert np.array_equal(env.agent.cpu().numpy().astype(np.uint32), ob.agent), where + " agent"
+    assert np.array_equal(env.goal.cpu().numpy().astype(np.uint32), ob.goal), where + " goal"
+    assert np.array_equal(env.t.cpu().numpy(), ob.t), where + " t"
+    assert np.array_equal(env.episode.cpu().numpy().astype(np.uint32), ob.episode), where + " episode"
+
+
+@pytest.mark.parametrize("size,kw", [
+    (21, {}),
+    (32, dict(selected_tasks=['ChopTree', 'BuildHouse'], number_of_tasks=2)),
+    (8, dict(stacking=False, selected_tasks=['MakeBread', 'EatBread', 'GoToHouse', 'MoveSticks'])),
+    (4, dict(number_of_tasks=3)),
+    (64, {}),
+])
+def test_reset_bit_exact_vs_oracle(cw, size, kw):
+    """Philox reset: placement, tasks, first frame, imagine_obs goal frame and INIT_OBS copy, over 3 episodes."""
+    N, seed = 300, 20240607
+    env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=seed, env_id_base=5000, **kw)
+    ob = oracle_for(env, seed)
+    for ep in range(3):
+        obs = env.reset()
+        goal = ob.reset(with_goal=True)
+        assert_env_equals_oracle(env, ob, f"{size}x{size} episode {ep}")
+        assert np.array_equal(obs["observation"].cpu().numpy(), ob.render())
+        assert np.array_equal(obs["desired_goal"].cpu().numpy(), goal)
+        assert np.array_equal(obs["init_observation"].cpu().numpy(), ob.render())
+        assert obs["achieved_goal"] is obs["observation"]                       # aliasing as upstream (ray.py:194-196)
+
+
+def test_masked_reset(cw):
+    N, seed = 257, 9
+    env = cw.BatchedCraftingWorldEnv(N, seed=seed)
+    ob = oracle_for(env, seed)
+    env.reset(); ob.reset(with_goal=True)
+    mask = (np.arange(N) % 3 == 0).astype(np.uint8)
+    before = env.obs.clone()
+    env.reset(mask=torch.from_numpy(mask).cuda())
+    ob.reset(mask=mask)
+    assert_env_equals_oracle(env, ob, "masked reset")
+    after = env.obs.cpu().numpy()
+    assert np.array_equal(after, ob.render())
+    assert np.array_equal(after[mask == 0], before.cpu().numpy()[mask == 0])
+
+
+@pytest.mark.parametrize("size,N,max_steps,K", [(21, 1000, 25, 120), (5, 513, 7, 60), (32, 200, 30, 70)])
+def test_autoreset_trajectory_vs_oracle(cw, size, N, max_steps, K):
+    """Fused step + auto-reset + render (+ goal / init frames + stats) against the C oracle's cwo_step_full,
+    every step: reward, done; every 10th step and at the end: full state and all three frame buffers."""
+    seed = 77
+    env = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=seed, auto_reset=True)
+    ob = oracle_for(env, seed)
+    env.reset()
+    o_goal = ob.reset(with_goal=True)
+    o_obs = ob.render()
+    o_init = o_obs.copy()
+    rng = np.random.RandomState(5)
+    for k in range(K):
+        a = rng.randint(0, 6, N).astype(np.uint8)
+        obs, reward, done, _ = env.step(torch.from_numpy(a).cuda())
+        new_goal = np.zeros_like(o_goal)
+        o_reward, o_done = ob.step_full(a, auto_reset=True, obs=o_obs, goal_obs=new_goal)
+        o_goal[o_done == 1] = new_goal[o_done == 1]
+        o_init[o_done == 1] = o_obs[o_done == 1]
+        assert np.array_equal(reward.cpu().numpy(), o_reward), f"step {k}"
+        assert np.array_equal(done.cpu().numpy(), o_done.astype(bool)), f"step {k}"
+        if k % 10 == 0 or k == K - 1:
+            assert_env_equals_oracle(env, ob, f"step {k}")
+            assert np.array_equal(obs["observation"].cpu().numpy(), o_obs), f"step {k} obs"
+            assert np.array_equal(obs["desired_goal"].cpu().numpy(), o_goal), f"step {k} goal frame"
+            assert np.array_equal(obs["init_observation"].cpu().numpy(), o_init), f"step {k} init frame"
+    assert np.array_equal(env.stats.cpu().numpy(), ob.stats)
+    st = env.episode_stats()
+    assert st["episodes"] == int(ob.stats[0]) > 0
+
+
+def test_autoreset_compact_and_rollout_vs_oracle(cw):
+    """Thread-per-world kernel with warp-cooperative auto-reset: single steps and a K-step rollout launch."""
+    N, seed, K = 2000, 31, 150
+    acts = np.random.RandomState(2).randint(0, 6, (K, N)).astype(np.uint8)
+    ob = None
+    for mode in ("steps", "rollout"):
+        env = cw.BatchedCraftingWorldEnv(N, size=(8, 8), max_steps=12, seed=seed, obs_mode="compact")
+        ob = oracle_for(env, seed)
+        env.reset(); ob.reset()
+        o_rew = np.zeros((K, N), np.int32); o_dn = np.zeros((K, N), np.uint8)
+        for k in range(K):
+            o_rew[k], o_dn[k] = ob.step_full(acts[k], auto_reset=True)
+        if mode == "steps":
+            for k in range(K):
+                _, reward, done, _ = env.step(acts[k])
+                assert np.array_equal(reward.cpu().numpy(), o_rew[k]) and np.array_equal(done.cpu().numpy(), o_dn[k].astype(bool))
+        else:
+            rew, dn = env.rollout(acts)
+            assert np.array_equal(rew.cpu().numpy(), o_rew) and np.array_equal(dn.cpu().numpy(), o_dn.astype(bool))
+        assert_env_equals_oracle(env, ob, mode)
+        assert np.array_equal(env.stats.cpu().numpy(), ob.stats), mode
+
+
+def test_fixed_init_state_pool(cw):
+    """fixed_init_state=n (ray.py:116-118, 630-644): every reset copies one of n pre-sampled worlds."""
+    N, seed, n_fixed = 400, 123, 5
+    env = cw.BatchedCraftingWorldEnv(N, size=(9, 9), fixed_init_state=n_fixed, seed=seed)
+    pool_g = env._fixed_grid.cpu().numpy()
+    pool_a = env._fixed_agent.cpu().numpy().astype(np.uint32)
+    # the pool itself is a Philox sample_state of streams FIXED_POOL_ID_BASE + i
+    pool_oracle = native.OracleBatch(native.make_config(H=9, W=9), n_fixed, seed=seed, env_id_base=1 << 62)
+    pool_oracle.reset()
+    assert np.array_equal(pool_g, pool_oracle.grid) and np.array_equal(pool_a, pool_oracle.agent)
+    ob = oracle_for(env, seed)
+    native.set_fixed_pool(pool_g, pool_a)
+    try:
+        for ep in range(2):
+            env.reset(); goal = ob.reset(with_goal=True)
+            assert_env_equals_oracle(env, ob, f"fixed pool episode {ep}")
+            assert np.array_equal(env.desired_goal.cpu().numpy(), goal)
+        grids = env.grid.cpu().numpy()
+        assert all(any(np.array_equal(g, p) for p in pool_g) for g in grids)
+        assert len({g.tobytes() for g in grids}) == n_fixed
+    finally:
+        native.set_fixed_pool(None)
+
+
+def test_imagine_on_injected_dense_worlds(cw):
+    """cw_imagine on injected (dense, possibly holding) worlds equals the oracle's imagine_obs + render."""
+    d = gu.load("dense_8x8.npz")
+    env = make_env(cw, d, goal_images=True)
+    env2 = oracle_for(env, 0)
+    env2.load_state(d["grid0"], d["r0"], d["c0"], d["hold0"], d["desired"])
+    ig, ia = env2.imagine()
+    tmp = native.OracleBatch(env2.cfg, env2.N)
+    tmp.grid[:], tmp.agent[:] = ig, ia
+    assert np.array_equal(env.desired_goal.cpu().numpy(), tmp.render())
+    assert np.array_equal(env.init_obs.cpu().numpy(), d["frame0"])
+
+
+def test_onehot_observation_vector(cw):
+    d = gu.load("dense_8x8.npz")
+    env = make_env(cw, d)
+    for t in range(8):
+        env.step(d["actions"][:, t])
+    oh = env.onehot().cpu().numpy()
+    s = env.export_state()
+    for b in range(env.num_envs):
+        want = ref_shim.compact_to_onehot(s["grid"][b], int(s["r"][b]), int(s["c"][b]), int(s["hold"][b]))
+        assert np.array_equal(oh[b], want.astype(np.uint8)), b
+    ov = env.observation_vector
+    assert ov["observation"].shape == (env.num_envs, 8, 8, 12) and ov["desired_goal"].shape == (env.num_envs, 9)
+
+
+def test_render_arbitrary_states(cw):
+    d = gu.load("dense_21x21.npz")
+    env = cw.BatchedCraftingWorldEnv(4, seed=0)
+    t = 31
+    out = env.render(state=(d["grid"][:, t], d["r"][:, t], d["c"][:, t], d["hold"][:, t])).cpu().numpy()
+    assert [gu.crc(f) for f in out] == list(d["frame_crc"][:, t])
+
+
+def test_sharding_does_not_change_worlds(cw):
+    """Worlds are keyed by GLOBAL id: two half-size envs with env_id_base offsets == one full env."""
+    N, seed, K = 512, 4242, 40
+    acts = np.random.RandomState(0).randint(0, 6, (K, N)).astype(np.uint8)
+    full = cw.BatchedCraftingWorldEnv(N, size=(6, 6), max_steps=9, seed=seed)
+    a = cw.BatchedCraftingWorldEnv(200, size=(6, 6), max_steps=9, seed=seed, env_id_base=0)
+    b = cw.BatchedCraftingWorldEnv(312, size=(6, 6), max_steps=9, seed=seed, env_id_base=200)
+    for e in (full, a, b):
+        e.reset()
+    for k in range(K):
+        full.step(acts[k]); a.step(acts[k, :200]); b.step(acts[k, 200:])
+    for key in ("grid", "agent", "goal", "t", "episode", "obs", "desired_goal", "init_obs"):
+        whole = getattr(full, key).cpu().numpy()
+        parts = np.concatenate([getattr(a, key).cpu().numpy(), getattr(b, key).cpu().numpy()])
+        assert np.array_equal(whole, parts), key
+    assert np.array_equal(full.stats.cpu().numpy(), (a.stats + b.stats).cpu().numpy())
+
+
+def test_invalid_actions(cw):
+    env = cw.BatchedCraftingWorldEnv(8, size=(5, 5), seed=1, auto_reset=False)
+    env.reset()
+    before = env.export_state()
+    _, reward, done, _ = env.step(torch.full((8,), 9, dtype=torch.uint8, device="cuda"))
+    after = env.export_state()
+    assert (reward.cpu().numpy() == -1).all() and not done.any()
+    assert np.array_equal(before["grid"], after["grid"]) and (after["t"] == 1).all()
+    strict = cw.BatchedCraftingWorldEnv(8, size=(5, 5), seed=1, validate_actions=True)
+    strict.reset()
+    with pytest.raises(IndexError):
+        strict.step(np.full(8, 6))
+    with pytest.raises(ValueError):
+        env.step(np.zeros(3, np.uint8))
+
+
+def test_api_surface_and_reward_helpers(cw):
+    env = cw.BatchedCraftingWorldEnv(16, seed=3)
+    assert env.action_space.n == 6 and env.observation_space["observation"].shape == (84, 84, 3)
+    assert env.observation_vector_space["observation"].shape == (21, 21, 12)
+    obs = env.reset()
+    assert set(obs) == {"observation", "desired_goal", "achieved_goal", "init_observation"}
+    assert obs["observation"].shape == (16, 84, 84, 3) and obs["observation"].dtype == torch.uint8
+    obs2, reward, done, info = env.step(torch.zeros(16, dtype=torch.int64, device="cuda"))
+    assert obs2["observation"] is obs["observation"]                               # owned + mutated in place
+    assert set(info) == {"task_success", "desired_goal", "achieved_goal"} and info["desired_goal"].shape == (16, 9)
+    assert reward.dtype == torch.int32 and done.dtype == torch.bool
+    assert env.seed(5) == [5]
+    ach = torch.tensor([[0, 1, 0, 0, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0, 0, 0, 0]], device="cuda")
+    des = torch.tensor([[0, 1, 0, 0, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0, 0, 0, 0]], device="cuda")
+    assert env.compute_reward_equal(ach, des).tolist() == [300, -1]
+    assert env.compute_reward_subset(ach, des).tolist() == [300, 300]
+    assert env.compute_reward(ach[0], des[0], None).tolist() == [300]
+
+
+def test_step_is_cuda_graph_capturable(cw):
+    N, K = 256, 16
+    acts = torch.from_numpy(np.random.RandomState(3).randint(0, 6, (K, N)).astype(np.uint8)).cuda()
+    ref = cw.BatchedCraftingWorldEnv(N, size=(7, 7), max_steps=10, seed=8)
+    env = cw.BatchedCraftingWorldEnv(N, size=(7, 7), max_steps=10, seed=8)
+    ref.reset(); env.reset()
+    for k in range(K):
+        ref.step(acts[k])
+    s = torch.cuda.Stream()                                   # (ref's steps above already warmed the launch path)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for k in range(K):
+                env.step(acts[k])
+    g.replay()
+    torch.cuda.synchronize()
+    for key in ("grid", "agent", "goal", "t", "episode", "obs", "desired_goal"):
+        assert torch.equal(getattr(env, key), getattr(ref, key)), key
+
+
+def test_host_env_matches_oracle(cw):
+    """The host-buffer API (cw_host_*): NumPy in / NumPy out, sliced + pipelined inside the library."""
+    N, seed, K = 3000, 55, 30
+    env = cw.HostCraftingWorldEnv(N, size=(21, 21), max_steps=15, seed=seed)
+    cfg = native.make_config(H=21, W=21, max_steps=15)
+    ob = native.OracleBatch(cfg, N, seed=seed)
+    obs = env.reset()
+    goal = ob.reset(with_goal=True)
+    o_obs = ob.render()
+    assert np.array_equal(obs["observation"], o_obs) and np.array_equal(obs["desired_goal"], goal)
+    rng = np.random.RandomState(1)
+    for k in range(K):
+        a = rng.randint(0, 6, N)
+        obs, reward, done, _ = env.step(a)
+        o_reward, o_done = ob.step_full(a.astype(np.uint8), auto_reset=True, obs=o_obs)
+        assert np.array_equal(reward, o_reward) and np.array_equal(done, o_done.astype(bool)), k
+        assert np.array_equal(obs["observation"], o_obs), k
+    assert np.array_equal(env.stats(), ob.stats)
+    env.close()

@@ -1,0 +1,86 @@
+"""CPU: host-side logic of the facade -- constructor-argument handling mirrors the reference (ray.py:59-83),
+sharding arithmetic, spaces metadata, and the no-CPU-fallback guarantee."""
+import numpy as np
+import pytest
+import torch
+
+import gym_craftingworld_b200 as cw
+from gym_craftingworld_b200 import spaces
+from gym_craftingworld_b200.env import make_config
+
+
+def test_default_config_matches_reference_defaults():
+    cfg = make_config()
+    assert (cfg.H, cfg.W, cfg.cell_stride, cfg.max_steps) == (21, 21, 448, 300)
+    assert (cfg.subset_reward, cfg.stacking, cfg.n_selected, cfg.number_of_tasks) == (0, 1, 9, 9)
+    assert list(cfg.selected)[:9] == list(range(9))
+    assert cw.TASK_LIST[4] == "ChopRock" and cw.TASK_LIST[8] == "MoveSticks"
+
+
+def test_number_of_tasks_is_clipped_like_upstream():
+    cfg = make_config(selected_tasks=["ChopTree", "BuildHouse"], number_of_tasks=5)     # ray.py:80-81
+    assert cfg.number_of_tasks == 2 and list(cfg.selected)[:2] == [3, 2]
+    assert make_config(reward_style="anything").subset_reward == 1                     # ray.py:71-74
+    assert make_config(stacking=1).stacking == 0                                       # `is True` upstream, ray.py:169
+    assert make_config(size=(32, 32)).cell_stride == 1024
+
+
+def test_task_bits_follow_task_list_index():
+    custom = list(reversed(cw.TASK_LIST))
+    cfg = make_config(task_list=custom, selected_tasks=["MakeBread"])                  # ray.py:174: task_list.index(...)
+    assert cfg.selected[0] == 8
+
+
+@pytest.mark.parametrize("kw", [dict(size=(21, 20)), dict(size=(2, 2)), dict(size=(65, 65)), dict(max_steps=0),
+                                dict(selected_tasks=["Fly"]), dict(selected_tasks=[]), dict(task_list=["a", "b"]),
+                                dict(number_of_tasks=0)])
+def test_bad_arguments_raise_value_error(kw):
+    with pytest.raises(ValueError):
+        make_config(**kw)
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, not degrade to a CPU implementation."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cw.BatchedCraftingWorldEnv(4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cw.HostCraftingWorldEnv(4)
+
+
+def test_unsupported_side_channels_are_explicit():
+    with pytest.raises(NotImplementedError):
+        cw.BatchedCraftingWorldEnv(4, store_gif=True)
+    with pytest.raises(ValueError):
+        cw.BatchedCraftingWorldEnv(4, obs_mode="ascii")
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    import re
+    pkg = os.path.dirname(cw.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "libcw_oracle" not in src, f
+
+
+def test_shard_range_partitions_exactly():
+    for total in (1, 7, 4096, 1 << 20, 1000003):
+        for world in (1, 2, 3, 8):
+            parts = [cw.shard_range(total, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and sum(n for _, n in parts) == total
+            for (lo, n), (lo2, _) in zip(parts, parts[1:]):
+                assert lo + n == lo2
+            assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
+
+
+def test_spaces_metadata():
+    d = spaces.Discrete(6)
+    assert d.n == 6 and all(0 <= d.sample() < 6 for _ in range(50)) and d.contains(5) and not d.contains(6)
+    b = spaces.Box(0, 255, (84, 84, 3), np.uint8)
+    assert b.shape == (84, 84, 3) and b.low == 0 and b.high == 255
+    assert spaces.Dict({"a": b})["a"] is b
