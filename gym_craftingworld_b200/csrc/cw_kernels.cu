@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) cw_onehot_kernel(const CwConfig cfg, cons
 // host side
 // ------------------------------------------------------------------------------------------------------
 struct OccEntry { int nbuf; size_t smem; int per_sm; };
-struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; int n_occ = 0; OccEntry occ[8]; };
+struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool attr_set[2] = {false, false}; int max_dyn = 0; int n_occ = 0; OccEntry occ[8]; };
 static DeviceInfo g_dev[64];
 
 static int device_info(DeviceInfo** out) {
@@ -292,16 +292,23 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     args.bands_per_chunk = needs_frame ? pick_bands(cfg, env_tunable("CW_CHUNK_BYTES", 25 * 1024)) : 1;
     args.w_magic = (uint32_t)(0x100000000ull / (uint64_t)cfg->W) + 1u;
     const size_t smem = 2 * (size_t)cfg->cell_stride + (needs_frame ? (size_t)nbuf * 48 * cfg->W * args.bands_per_chunk : 0);
-    if (smem > (size_t)dev->smem_optin) return CW_E_BADCONFIG;
     auto kern = nbuf == 2 ? cw_env_kernel<2> : cw_env_kernel<1>;
-    // occupancy is queried once per (device, buffers, smem size); the attribute call is also skipped afterwards
+    // occupancy is queried once per (device, buffers, smem size)
     int per_sm = 0;
     for (int i = 0; i < dev->n_occ; i++)
         if (dev->occ[i].nbuf == nbuf && dev->occ[i].smem == smem) per_sm = dev->occ[i].per_sm;
-    if (per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!dev->attr_set[nbuf - 1]) {   // once per device and kernel: allow any dynamic size up to the opt-in maximum
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
         if (e != cudaSuccess) return (int)e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+        dev->max_dyn = dev->smem_optin - (int)fa.sharedSizeBytes;   // the opt-in limit covers static + dynamic
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev->max_dyn);
+        if (e != cudaSuccess) return (int)e;
+        dev->attr_set[nbuf - 1] = true;
+    }
+    if (smem > (size_t)dev->max_dyn) return CW_E_BADCONFIG;
+    if (per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
         if (e != cudaSuccess) return (int)e;
         if (per_sm < 1) per_sm = 1;
         if (dev->n_occ < 8) { dev->occ[dev->n_occ].nbuf = nbuf; dev->occ[dev->n_occ].smem = smem; dev->occ[dev->n_occ].per_sm = per_sm; dev->n_occ++; }
