@@ -383,15 +383,16 @@ __device__ __forceinline__ void compose_bands(const CwConfig& cfg, const uint8_t
         const uint32_t rgb = slut[src[i]];
         const uint32_t w0 = __byte_perm(rgb, 0, 0x0210), w1 = __byte_perm(rgb, 0, 0x1021), w2 = __byte_perm(rgb, 0, 0x2102);
         uint32_t* p = frame + b * (4 * roww) + 3 * col;
-        const bool isa = i == acell;
         p[0] = w0; p[1] = w1; p[2] = w2;
-        p[roww + 0] = isa ? (w0 | 0xFF000000u) : w0;
-        p[roww + 1] = isa ? 0xFFFFFFFFu : w1;
-        p[roww + 2] = isa ? (w2 | 0x000000FFu) : w2;
-        p[2 * roww + 0] = isa ? __byte_perm(w0, hc, 0x4210) : w0;
-        p[2 * roww + 1] = isa ? __byte_perm(hc, 0, 0x1021) : w1;
-        p[2 * roww + 2] = isa ? __byte_perm(w2, hc, 0x3216) : w2;
+        p[roww + 0] = w0; p[roww + 1] = w1; p[roww + 2] = w2;
+        p[2 * roww + 0] = w0; p[2 * roww + 1] = w1; p[2 * roww + 2] = w2;
         p[3 * roww + 0] = w0; p[3 * roww + 1] = w1; p[3 * roww + 2] = w2;
+        if (i == acell) {                                      // one thread per frame: agent overlay (ray.py:483-486)
+            p[roww + 0] = w0 | 0xFF000000u; p[roww + 1] = 0xFFFFFFFFu; p[roww + 2] = w2 | 0x000000FFu;
+            p[2 * roww + 0] = __byte_perm(w0, hc, 0x4210);
+            p[2 * roww + 1] = __byte_perm(hc, 0, 0x1021);
+            p[2 * roww + 2] = __byte_perm(w2, hc, 0x3216);
+        }
     }
 }
 
@@ -406,5 +407,17 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int kPending>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_dyn(int pending) {   // pending in 0..2
+    if (pending <= 0) bulk_wait_read<0>();
+    else if (pending == 1) bulk_wait_read<1>();
+    else bulk_wait_read<2>();
+}
+// 16-byte async copy global -> shared through L2 (LDGSTS), for the grid tiles
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 }  // namespace cw

@@ -33,134 +33,176 @@ struct EnvArgs {
     const uint8_t* rgrid;    // render-only entry: grid / agent given directly (state may be partial)
     const uint32_t* ragent;
     int mode;
+    int group;               // G: worlds per CTA iteration (<= 32); their steps run lane-parallel in warp 0
+    int nbuf;                // F: frame-chunk ring slots (2..4)
     int bands_per_chunk;
     uint32_t w_magic;        // floor(2^32 / W) + 1
 };
 
-// dynamic shared memory: [sgrid cell_stride][simag cell_stride][frame: kBuf * chunk_bytes]
-template <int kBuf>
-__global__ void __launch_bounds__(128) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
+enum : int { FL_RENDER = 1, FL_FRESH = 2, FL_GOAL = 4 };
+
+// One CTA iteration handles a GROUP of G consecutive worlds:
+//   A  grid tiles of the group arrive in shared memory (cp.async, prefetched one group ahead; scalars are
+//      prefetched into registers of warp 0, lane i = world i of the group)
+//   B  warp 0 steps the G worlds lane-parallel on the shared tiles, then re-seeds finished / forced worlds
+//      cooperatively (Philox reset + imagine_obs into a scratch tile)
+//   C  all 4 warps expand one world at a time into a ring of F frame slots; thread 0 streams each slot out with
+//      a TMA bulk store and only waits for the store issued F-1 slots earlier, so composing overlaps the stores.
+// dynamic shared memory: [tiles 2 x G x cell_stride][imagine scratch G x cell_stride][ring F x chunk_bytes]
+__global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_lut[9];
-    __shared__ uint32_t s_agent, s_goal_agent;
-    __shared__ int s_reset;
+    __shared__ uint32_t s_agent[32], s_gagent[32];
+    __shared__ uint32_t s_flag[32];
 
-    uint8_t* sgrid = smem;
-    uint8_t* simag = smem + cfg.cell_stride;
-    const int H = cfg.H, W = cfg.W;
+    const int H = cfg.H, W = cfg.W, cs = cfg.cell_stride;
+    const int G = args.group, F = args.nbuf, mode = args.mode;
     const uint32_t band_bytes = 48u * (uint32_t)W;                // 4 pixel rows x 4W pixels x 3 bytes
     const uint32_t chunk_bytes = band_bytes * (uint32_t)args.bands_per_chunk;
     const size_t frame_bytes = (size_t)band_bytes * H;
-    uint8_t* fbuf = smem + 2 * cfg.cell_stride;
+    uint8_t* tiles = smem;
+    uint8_t* simag = smem + 2 * G * cs;
+    uint8_t* ring = smem + 3 * G * cs;
     const int tid = threadIdx.x;
-    const int nchunk16 = cfg.cell_stride >> 4;
-    const int mode = args.mode;
+    const int nchunk16 = cs >> 4;
     const uint8_t* grid_in = args.rgrid ? args.rgrid : st.grid;
     const uint32_t* agent_in = args.ragent ? args.ragent : st.agent;
+    const int64_t ngroups = (st.n + G - 1) / G;
 
     if (tid < 9) s_lut[tid] = kColorLUT[tid];
-    int buf = 0;
 
-    for (int64_t n = blockIdx.x; n < st.n; n += gridDim.x) {
-        const bool forced = (mode & M_FORCE_RESET) && (!args.mask || args.mask[n]);
-        if ((mode & M_FORCE_RESET) && !forced) continue;          // masked reset: untouched worlds are skipped
-        // ---- A: stage the grid tile; thread 0 fetches the scalars --------------------------------------
-        if (!forced && tid < nchunk16)
-            reinterpret_cast<uint4*>(sgrid)[tid] = reinterpret_cast<const uint4*>(grid_in + n * cfg.cell_stride)[tid];
-        uint32_t agent = 0, goal = 0;
-        int t = 0, a = 6;
-        if (tid == 0) {
-            agent = agent_in[n];
-            if (mode & (M_STEP | M_IMAGINE_ONLY)) goal = st.goal[n];
-            if (mode & M_STEP) { t = st.t[n]; a = args.actions[n]; }
-            if (kBuf == 1) bulk_wait_read<0>(); else bulk_wait_read<kBuf - 1>();   // frame buffer `buf` is free again
+    // tile + scalar prefetch of group `g` (tiles -> stage `sgi`; scalars -> registers of warp 0)
+    uint32_t p_agent = 0, p_goal = 0;
+    int p_t = 0, p_a = 6, p_forced = 0;
+    auto prefetch = [&](int64_t g, int sgi) {
+        if (g < ngroups) {
+            const int64_t e0 = g * G;
+            const int cnt = (int)min((int64_t)G, st.n - e0);
+            const uint8_t* src = grid_in + e0 * cs;
+            uint8_t* dst = tiles + (size_t)sgi * G * cs;
+            for (int i = tid; i < cnt * nchunk16; i += blockDim.x) cp_async16(dst + 16 * i, src + 16 * i);
+            if (tid < cnt) {
+                const int64_t e = e0 + tid;
+                p_agent = agent_in[e];
+                if (mode & (M_STEP | M_IMAGINE_ONLY)) p_goal = st.goal[e];
+                if (mode & M_STEP) { p_t = st.t[e]; p_a = args.actions[e]; }
+                if (mode & M_FORCE_RESET) p_forced = (!args.mask || args.mask[e]) ? 1 : 0;
+            }
         }
+        cp_async_commit();
+    };
+
+    uint32_t q = 0;                                               // frame-chunk sequence number (ring slot = q % F)
+    int slot = 0;
+    // expand one world (tile `src`) into the ring and stream it to dst (and dst2 when non-null)
+    auto emit_frame = [&](const uint8_t* src, uint32_t ag, uint8_t* dst, uint8_t* dst2) {
+        for (int band0 = 0; band0 < H; band0 += args.bands_per_chunk) {
+            const int nb = min(args.bands_per_chunk, H - band0);
+            uint8_t* fb = ring + (size_t)slot * chunk_bytes;
+            compose_bands(cfg, src, ag, band0, nb, reinterpret_cast<uint32_t*>(fb), s_lut, args.w_magic);
+            fence_proxy_async_smem();
+            if (tid == 0) bulk_wait_read_dyn(F - 2);              // frees the slot the NEXT chunk composes into
+            __syncthreads();
+            if (tid == 0) {
+                bulk_store(dst + (size_t)band0 * band_bytes, fb, band_bytes * nb);
+                if (dst2) bulk_store(dst2 + (size_t)band0 * band_bytes, fb, band_bytes * nb);
+                bulk_commit();
+            }
+            q++;
+            slot = (slot + 1 == F) ? 0 : slot + 1;
+        }
+    };
+
+    int stage = 0;
+    prefetch(blockIdx.x, 0);
+    for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
+        // ---- A: this group's scalars move to `c_*`; the next group's tiles + scalars start loading ------------
+        const uint32_t c_agent = p_agent, c_goal = p_goal;
+        const int c_t = p_t, c_a = p_a, c_forced = p_forced;
+        prefetch(gi + gridDim.x, stage ^ 1);
+        cp_async_wait<1>();                                       // everything but the newest group has landed
         __syncthreads();
-        // ---- B: step (one thread; every cell it needs is in shared memory, init cells in L2) -----------
-        if (tid == 0) {
-            int do_reset = forced ? 1 : 0;
-            if (mode & M_STEP) {
-                bool dn; int wcell, wval;
-                const int rew = step_core(cfg, sgrid, st.init_grid + n * cfg.cell_stride, agent, goal, t, a, dn, wcell, wval);
-                if (wcell >= 0) st.grid[n * cfg.cell_stride + wcell] = (uint8_t)wval;
-                args.reward[n] = rew;
-                args.done[n] = dn ? 1 : 0;
-                if (dn && (mode & M_AUTO_RESET)) {
-                    do_reset = 1;
-                    if (args.stats) stats_add(cfg, args.stats, goal, t, rew);
-                } else {
-                    st.agent[n] = agent; st.goal[n] = goal; st.t[n] = t;
+        uint8_t* gt = tiles + (size_t)stage * G * cs;             // this group's tiles
+        const int64_t e0 = gi * G;
+        // ---- B: warp 0 steps the group lane-parallel, then re-seeds worlds cooperatively ----------------------
+        if (tid < 32) {
+            const int lane = tid;
+            const int64_t e = e0 + lane;
+            const bool valid = lane < G && e < st.n;
+            uint32_t agent = c_agent, goal = c_goal, flag = 0;
+            bool do_reset = false;
+            if (valid) {
+                const bool skip = (mode & M_FORCE_RESET) && !c_forced;   // masked reset: untouched worlds are skipped
+                if (!skip && (mode & M_RENDER)) flag |= FL_RENDER;
+                do_reset = (mode & M_FORCE_RESET) && c_forced;
+                if (mode & M_STEP) {
+                    int t = c_t, wcell, wval;
+                    bool dn;
+                    const int rew = step_core(cfg, gt + lane * cs, st.init_grid + e * cs, agent, goal, t, c_a, dn, wcell, wval);
+                    if (wcell >= 0) st.grid[e * cs + wcell] = (uint8_t)wval;
+                    args.reward[e] = rew;
+                    args.done[e] = dn ? 1 : 0;
+                    if (dn && (mode & M_AUTO_RESET)) {
+                        do_reset = true;
+                        if (args.stats) stats_add(cfg, args.stats, goal, t, rew);
+                    } else {
+                        st.agent[e] = agent; st.goal[e] = goal; st.t[e] = t;
+                    }
                 }
             }
-            s_agent = agent; s_goal_agent = goal;                 // s_goal_agent carries `goal` into phase C
-            s_reset = do_reset;
-        }
-        __syncthreads();
-        // ---- C: reset (+ goal frame) by warp 0 ----------------------------------------------------------
-        const bool resetting = s_reset != 0;
-        const bool imagining = (resetting && args.goal_obs) || (mode & M_IMAGINE_ONLY);
-        if (resetting || imagining) {
-            if (tid < 32) {
+            uint32_t m = __ballot_sync(0xffffffffu, valid && do_reset);
+            while (m) {                                           // reset(): ray.py:156-218, one world at a time
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int64_t er = e0 + src;
                 WarpPhilox rng;
-                uint32_t ag = s_agent, gl = s_goal_agent;
-                if (resetting) {
-                    reset_warp(cfg, st, n, sgrid, rng, ag, gl);
-                    if (tid == 0) { st.agent[n] = ag; st.goal[n] = gl; st.t[n] = 0; s_agent = ag; }
-                } else {
-                    rng.init(st.seed, st.env_id_base + (uint64_t)n, st.episode[n]);
-                }
-                if (imagining) {
-                    for (int ch = tid; ch < nchunk16; ch += 32)
-                        reinterpret_cast<uint4*>(simag)[ch] = reinterpret_cast<const uint4*>(sgrid)[ch];
+                uint32_t ag, gl;
+                reset_warp(cfg, st, er, gt + src * cs, rng, ag, gl);
+                if (lane == src) { agent = ag; goal = gl; st.agent[er] = ag; st.goal[er] = gl; st.t[er] = 0; flag |= FL_FRESH; }
+                if (args.goal_obs) {                              // desired_goal = imagine_obs(): ray.py:191, 220-299
+                    uint8_t* im = simag + src * cs;
+                    for (int ch = lane; ch < nchunk16; ch += 32)
+                        reinterpret_cast<uint4*>(im)[ch] = reinterpret_cast<const uint4*>(gt + src * cs)[ch];
                     __syncwarp();
                     uint32_t gag = ag;
-                    imagine_warp(cfg, simag, gag, gl >> 16, rng);
-                    if (tid == 0) s_goal_agent = gag;
+                    imagine_warp(cfg, im, gag, gl >> 16, rng);
+                    if (lane == src) { s_gagent[src] = gag; flag |= FL_GOAL; }
                 }
             }
-            __syncthreads();
-            if (imagining) {                                      // goal frame: rare path, chunks serialised
-                uint8_t* gdst = args.goal_obs + (size_t)n * frame_bytes;
-                for (int band0 = 0; band0 < H; band0 += args.bands_per_chunk) {
-                    const int nb = min(args.bands_per_chunk, H - band0);
-                    if (tid == 0) bulk_wait_read<0>();
-                    __syncthreads();
-                    compose_bands(cfg, simag, s_goal_agent, band0, nb, reinterpret_cast<uint32_t*>(fbuf), s_lut, args.w_magic);
-                    fence_proxy_async_smem();
-                    __syncthreads();
-                    if (tid == 0) { bulk_store(gdst + (size_t)band0 * band_bytes, fbuf, band_bytes * nb); bulk_commit(); }
+            if (mode & M_IMAGINE_ONLY) {                          // goal frame of the current (injected) state
+                m = __ballot_sync(0xffffffffu, valid);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int64_t er = e0 + src;
+                    WarpPhilox rng;
+                    rng.init(st.seed, st.env_id_base + (uint64_t)er, st.episode[er]);
+                    uint8_t* im = simag + src * cs;
+                    for (int ch = lane; ch < nchunk16; ch += 32)
+                        reinterpret_cast<uint4*>(im)[ch] = reinterpret_cast<const uint4*>(gt + src * cs)[ch];
+                    __syncwarp();
+                    uint32_t gag = __shfl_sync(0xffffffffu, agent, src);
+                    const uint32_t gl = __shfl_sync(0xffffffffu, goal, src);
+                    imagine_warp(cfg, im, gag, gl >> 16, rng);
+                    if (lane == src) { s_gagent[src] = gag; flag |= FL_GOAL; }
                 }
-                if (tid == 0) bulk_wait_read<0>();
-                __syncthreads();
-                buf = 0;
             }
+            if (lane < G) { s_agent[lane] = agent; s_flag[lane] = valid ? flag : 0; }
         }
-        // ---- D: render the (possibly fresh) state: compose in shared memory, TMA bulk store -------------
-        if (mode & M_RENDER) {
-            const uint32_t ag = s_agent;
-            uint8_t* gdst = args.obs + (size_t)n * frame_bytes;
-            for (int band0 = 0; band0 < H; band0 += args.bands_per_chunk) {
-                const int nb = min(args.bands_per_chunk, H - band0);
-                uint8_t* fb = fbuf + (size_t)buf * chunk_bytes;
-                if (band0 > 0) {                                  // further chunks of the same world
-                    if (tid == 0) { if (kBuf == 1) bulk_wait_read<0>(); else bulk_wait_read<kBuf - 1>(); }
-                    __syncthreads();
-                }
-                compose_bands(cfg, sgrid, ag, band0, nb, reinterpret_cast<uint32_t*>(fb), s_lut, args.w_magic);
-                fence_proxy_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    bulk_store(gdst + (size_t)band0 * band_bytes, fb, band_bytes * nb);
-                    if (resetting && args.init_obs)               // same chunk, second destination
-                        bulk_store(args.init_obs + (size_t)n * frame_bytes + (size_t)band0 * band_bytes, fb, band_bytes * nb);
-                    bulk_commit();
-                }
-                buf = (buf + 1 == kBuf) ? 0 : buf + 1;
-            }
-        } else {
-            __syncthreads();                                      // sgrid / s_* are rewritten next iteration
+        __syncthreads();
+        // ---- C: expand + stream out, one world at a time -----------------------------------------------------
+        for (int i = 0; i < G; i++) {
+            const uint32_t flag = s_flag[i];
+            if (!flag) continue;
+            const size_t off = (size_t)(e0 + i) * frame_bytes;
+            if (flag & FL_GOAL) emit_frame(simag + i * cs, s_gagent[i], args.goal_obs + off, nullptr);
+            if (flag & FL_RENDER)
+                emit_frame(gt + i * cs, s_agent[i], args.obs + off, ((flag & FL_FRESH) && args.init_obs) ? args.init_obs + off : nullptr);
         }
+        __syncthreads();                                          // tiles / s_* of this stage are rewritten next
+        stage ^= 1;
     }
+    cp_async_wait<0>();
     if (tid == 0) bulk_wait_all();
 }
 
@@ -230,8 +272,8 @@ __global__ void __launch_bounds__(256) cw_onehot_kernel(const CwConfig cfg, cons
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-struct OccEntry { int nbuf; size_t smem; int per_sm; };
-struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool attr_set[2] = {false, false}; int max_dyn = 0; int n_occ = 0; OccEntry occ[8]; };
+struct OccEntry { size_t smem; int per_sm; };
+struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool attr_set = false; int max_dyn = 0; int n_occ = 0; OccEntry occ[64]; };
 static DeviceInfo g_dev[64];
 
 static int device_info(DeviceInfo** out) {
@@ -287,36 +329,57 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     int rc = device_info(&dev);
     if (rc) return rc;
     if (st->n <= 0) return 0;
-    const int nbuf = env_tunable("CW_FRAME_BUFFERS", 1) >= 2 ? 2 : 1;
-    const bool needs_frame = (args.mode & M_RENDER) || args.goal_obs;
-    args.bands_per_chunk = needs_frame ? pick_bands(cfg, env_tunable("CW_CHUNK_BYTES", 25 * 1024)) : 1;
-    args.w_magic = (uint32_t)(0x100000000ull / (uint64_t)cfg->W) + 1u;
-    const size_t smem = 2 * (size_t)cfg->cell_stride + (needs_frame ? (size_t)nbuf * 48 * cfg->W * args.bands_per_chunk : 0);
-    auto kern = nbuf == 2 ? cw_env_kernel<2> : cw_env_kernel<1>;
-    // occupancy is queried once per (device, buffers, smem size)
-    int per_sm = 0;
-    for (int i = 0; i < dev->n_occ; i++)
-        if (dev->occ[i].nbuf == nbuf && dev->occ[i].smem == smem) per_sm = dev->occ[i].per_sm;
-    if (!dev->attr_set[nbuf - 1]) {   // once per device and kernel: allow any dynamic size up to the opt-in maximum
+    auto kern = cw_env_kernel;
+    if (!dev->attr_set) {   // once per device: allow any dynamic size up to the opt-in maximum, prefer shared memory
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, kern);
         if (e != cudaSuccess) return (int)e;
         dev->max_dyn = dev->smem_optin - (int)fa.sharedSizeBytes;   // the opt-in limit covers static + dynamic
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev->max_dyn);
         if (e != cudaSuccess) return (int)e;
-        dev->attr_set[nbuf - 1] = true;
-    }
-    if (smem > (size_t)dev->max_dyn) return CW_E_BADCONFIG;
-    if (per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        if (per_sm < 1) per_sm = 1;
-        if (dev->n_occ < 8) { dev->occ[dev->n_occ].nbuf = nbuf; dev->occ[dev->n_occ].smem = smem; dev->occ[dev->n_occ].per_sm = per_sm; dev->n_occ++; }
+        dev->attr_set = true;
     }
+    const bool needs_frame = (args.mode & M_RENDER) || args.goal_obs;
+    int F = env_tunable("CW_FRAME_BUFFERS", 2);
+    F = F < 2 ? 2 : (F > 4 ? 4 : F);
+    args.nbuf = F;
+    args.bands_per_chunk = needs_frame ? pick_bands(cfg, env_tunable("CW_CHUNK_BYTES", 25 * 1024)) : 1;
+    args.w_magic = (uint32_t)(0x100000000ull / (uint64_t)cfg->W) + 1u;
+    const size_t ring = needs_frame ? (size_t)F * 48 * cfg->W * args.bands_per_chunk : 0;
     const int cap = env_tunable("CW_CTAS_PER_SM", 0);
-    if (cap > 0 && cap < per_sm) per_sm = cap;
-    int64_t blocks = (int64_t)dev->sms * per_sm;
-    if (blocks > st->n) blocks = st->n;
+    // group size G: the per-SM critical path is (CTA waves) x G worlds; pick the G that minimises it
+    int bestG = 0, best_per_sm = 1;
+    int64_t best_cost = 0;
+    const int forcedG = env_tunable("CW_GROUP", 0);
+    const int gmax = 16384 / cfg->cell_stride < 1 ? 1 : (16384 / cfg->cell_stride > 16 ? 16 : 16384 / cfg->cell_stride);
+    for (int G = (forcedG > 0 ? forcedG : 1); G <= (forcedG > 0 ? forcedG : gmax); G++) {
+        if (G > 32) break;
+        const size_t smem = 3 * (size_t)G * cfg->cell_stride + ring;
+        if (smem > (size_t)dev->max_dyn) break;
+        int per_sm = 0;
+        for (int i = 0; i < dev->n_occ; i++)
+            if (dev->occ[i].smem == smem) per_sm = dev->occ[i].per_sm;
+        if (per_sm == 0) {
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+            if (e != cudaSuccess) return (int)e;
+            if (per_sm < 1) per_sm = 1;
+            if (dev->n_occ < 64) { dev->occ[dev->n_occ].smem = smem; dev->occ[dev->n_occ].per_sm = per_sm; dev->n_occ++; }
+        }
+        if (cap > 0 && cap < per_sm) per_sm = cap;
+        const int64_t slots = (int64_t)dev->sms * per_sm;
+        const int64_t groups = (st->n + G - 1) / G;
+        const int64_t waves = (groups + slots - 1) / slots;
+        const int64_t cost = waves * G + waves;                  // + a fixed per-wave cost (load / step latency)
+        if (bestG == 0 || cost < best_cost || (cost == best_cost && G > bestG)) { bestG = G; best_cost = cost; best_per_sm = per_sm; }
+    }
+    if (bestG == 0) return CW_E_BADCONFIG;
+    args.group = bestG;
+    const size_t smem = 3 * (size_t)bestG * cfg->cell_stride + ring;
+    int64_t blocks = (int64_t)dev->sms * best_per_sm;
+    const int64_t groups = (st->n + bestG - 1) / bestG;
+    if (blocks > groups) blocks = groups;
     kern<<<(unsigned)blocks, 128, smem, stream>>>(*cfg, *st, args);
     return (int)cudaGetLastError();
 }
