@@ -69,7 +69,11 @@ __global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, cons
     const uint32_t* agent_in = args.ragent ? args.ragent : st.agent;
     const int64_t ngroups = (st.n + G - 1) / G;
 
+    // Programmatic dependent launch: let the next launch in the stream start its prologue now, and do not touch
+    // anything the previous launch wrote (state, frames) until it has fully completed.
+    pdl_launch_dependents();
     if (tid < 9) s_lut[tid] = kColorLUT[tid];
+    pdl_wait();
 
     // tile + scalar prefetch of group `g` (tiles -> stage `sgi`; scalars -> registers of warp 0)
     uint32_t p_agent = 0, p_goal = 0;
@@ -210,6 +214,8 @@ __global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, cons
 __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
                                                       int32_t* __restrict__ reward, uint8_t* __restrict__ done,
                                                       unsigned long long* stats, int K, int flags) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = n < st.n;
     const int64_t nn = valid ? n : 0;
@@ -308,6 +314,21 @@ static int check_reset_config(const CwConfig* cfg) {
     return (cfg->H * cfg->W >= 9) ? 0 : CW_E_BADCONFIG;   // 9 distinct cells are needed (the reference needs 12, ray.py:608)
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL): back-to-back launches of the step graph
+// overlap the next kernel's launch + prologue with this kernel's tail.  CW_PDL=0 disables it.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    static int use_pdl = -1;
+    if (use_pdl < 0) { const char* e = getenv("CW_PDL"); use_pdl = (e && *e == '0') ? 0 : 1; }
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);
+}
+
 static int env_tunable(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
@@ -380,8 +401,8 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     int64_t blocks = (int64_t)dev->sms * best_per_sm;
     const int64_t groups = (st->n + bestG - 1) / bestG;
     if (blocks > groups) blocks = groups;
-    kern<<<(unsigned)blocks, 128, smem, stream>>>(*cfg, *st, args);
-    return (int)cudaGetLastError();
+    cudaError_t le = launch_pdl(kern, dim3((unsigned)blocks), dim3(128), smem, stream, *cfg, *st, args);
+    return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 }  // namespace cw
@@ -439,9 +460,9 @@ int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, i
     if (st->n == 0 || K == 0) return 0;
     if (!actions) return CW_E_NULLPTR;
     const int64_t blocks = (st->n + 127) / 128;
-    cw_step_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*cfg, *st, actions, reward, done,
-                                                                        (unsigned long long*)stats, K, flags);
-    return (int)cudaGetLastError();
+    cudaError_t le = launch_pdl(cw_step_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions,
+                                reward, done, (unsigned long long*)stats, K, flags);
+    return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 int cw_render(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, uint8_t* obs, int64_t n, void* stream) {
