@@ -76,10 +76,13 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
     TRY(cudaMalloc(&e->st.grid, gb)); TRY(cudaMalloc(&e->st.init_grid, gb));
     TRY(cudaMalloc(&e->st.agent, n * 4)); TRY(cudaMalloc(&e->st.goal, n * 4));
     TRY(cudaMalloc(&e->st.t, n * 4)); TRY(cudaMalloc(&e->st.episode, n * 4));
-    TRY(cudaMalloc(&e->d_actions, n)); TRY(cudaMalloc(&e->d_done, n)); TRY(cudaMalloc(&e->d_reward, n * 4));
+    TRY(cudaMalloc(&e->d_actions, n));
+    TRY(cudaMalloc(&e->d_reward, n * 5));                       // [reward int32 x n][done uint8 x n], one block
+    if (!rc) e->d_done = reinterpret_cast<uint8_t*>(e->d_reward) + n * 4;
     TRY(cudaMalloc(&e->d_obs, (size_t)n * e->frame_bytes)); TRY(cudaMalloc(&e->d_goal_obs, (size_t)n * e->frame_bytes));
     TRY(cudaMalloc(&e->d_stats, CW_STATS_LEN * 8));
-    TRY(cudaMallocHost(&e->h_actions, n)); TRY(cudaMallocHost(&e->h_done, n)); TRY(cudaMallocHost(&e->h_reward, n * 4));
+    TRY(cudaMallocHost(&e->h_actions, n)); TRY(cudaMallocHost(&e->h_reward, n * 5));
+    if (!rc) e->h_done = reinterpret_cast<uint8_t*>(e->h_reward) + n * 4;
     TRY(cudaMallocHost(&e->h_stats, CW_STATS_LEN * 8));
     TRY(cudaStreamCreateWithFlags(&e->streams[0], cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&e->streams[1], cudaStreamNonBlocking));
@@ -133,24 +136,34 @@ int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host
     if (obs_host && !direct) { int rc = ensure_frame_staging(e); if (rc) return rc; frames_dst = e->h_frames; }
     const uint8_t* act_src = actions_host;
     if (!is_pinned(actions_host)) { memcpy(e->h_actions, actions_host, n); act_src = e->h_actions; }
-    int k = 0;
-    for (int64_t off = 0; off < n; off += e->slice, k ^= 1) {
-        const int64_t cnt = (n - off) < e->slice ? (n - off) : e->slice;
-        cudaStream_t s = e->streams[k];
-        CK(cudaMemcpyAsync(e->d_actions + off, act_src + off, cnt, cudaMemcpyHostToDevice, s));
-        CwState sl = slice_state(e, off, cnt);
-        int rc = cw_step_render(&e->cfg, &sl, e->d_actions + off, e->d_reward + off, e->d_done + off,
-                                e->d_obs + (size_t)off * e->frame_bytes, e->d_goal_obs + (size_t)off * e->frame_bytes, nullptr,
+    if (!obs_host) {
+        // frames stay in HBM for a device-side consumer: one launch, one 5n-byte copy back, one sync
+        cudaStream_t s = e->streams[0];
+        CK(cudaMemcpyAsync(e->d_actions, act_src, n, cudaMemcpyHostToDevice, s));
+        int rc = cw_step_render(&e->cfg, &e->st, e->d_actions, e->d_reward, e->d_done, e->d_obs, e->d_goal_obs, nullptr,
                                 e->d_stats, e->flags, s);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(e->h_reward + off, e->d_reward + off, cnt * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(e->h_done + off, e->d_done + off, cnt, cudaMemcpyDeviceToHost, s));
-        if (obs_host)
+        CK(cudaMemcpyAsync(e->h_reward, e->d_reward, n * 5, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    } else {
+        int k = 0;
+        for (int64_t off = 0; off < n; off += e->slice, k ^= 1) {
+            const int64_t cnt = (n - off) < e->slice ? (n - off) : e->slice;
+            cudaStream_t s = e->streams[k];
+            CK(cudaMemcpyAsync(e->d_actions + off, act_src + off, cnt, cudaMemcpyHostToDevice, s));
+            CwState sl = slice_state(e, off, cnt);
+            int rc = cw_step_render(&e->cfg, &sl, e->d_actions + off, e->d_reward + off, e->d_done + off,
+                                    e->d_obs + (size_t)off * e->frame_bytes, e->d_goal_obs + (size_t)off * e->frame_bytes, nullptr,
+                                    e->d_stats, e->flags, s);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(e->h_reward + off, e->d_reward + off, cnt * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(e->h_done + off, e->d_done + off, cnt, cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(frames_dst + (size_t)off * e->frame_bytes, e->d_obs + (size_t)off * e->frame_bytes,
                                (size_t)cnt * e->frame_bytes, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(e->streams[0]));
+        CK(cudaStreamSynchronize(e->streams[1]));
     }
-    CK(cudaStreamSynchronize(e->streams[0]));
-    CK(cudaStreamSynchronize(e->streams[1]));
     memcpy(reward_host, e->h_reward, n * 4);
     memcpy(done_host, e->h_done, n);
     if (obs_host && !direct) memcpy(obs_host, e->h_frames, (size_t)n * e->frame_bytes);
@@ -178,9 +191,9 @@ int cw_host_destroy(CwHostEnv* e) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     cudaSetDevice(e->device);
     cudaFree(e->st.grid); cudaFree(e->st.init_grid); cudaFree(e->st.agent); cudaFree(e->st.goal); cudaFree(e->st.t);
-    cudaFree(e->st.episode); cudaFree(e->d_actions); cudaFree(e->d_done); cudaFree(e->d_reward); cudaFree(e->d_obs);
+    cudaFree(e->st.episode); cudaFree(e->d_actions); cudaFree(e->d_reward); cudaFree(e->d_obs);
     cudaFree(e->d_goal_obs); cudaFree(e->d_stats);
-    cudaFreeHost(e->h_actions); cudaFreeHost(e->h_done); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_stats);
+    cudaFreeHost(e->h_actions); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_stats);
     if (e->h_frames) cudaFreeHost(e->h_frames);
     if (e->streams[0]) cudaStreamDestroy(e->streams[0]);
     if (e->streams[1]) cudaStreamDestroy(e->streams[1]);
