@@ -137,13 +137,13 @@ int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host
     const uint8_t* act_src = actions_host;
     if (!is_pinned(actions_host)) { memcpy(e->h_actions, actions_host, n); act_src = e->h_actions; }
     if (!obs_host) {
-        // frames stay in HBM for a device-side consumer: one launch, one 5n-byte copy back, one sync
+        // Frames stay in HBM for a device-side consumer.  Zero-copy: the kernel reads the actions from, and writes
+        // reward/done to, mapped pinned host memory (UVA), so a step is ONE launch + ONE stream sync -- no memcpy
+        // launches on the critical path.
         cudaStream_t s = e->streams[0];
-        CK(cudaMemcpyAsync(e->d_actions, act_src, n, cudaMemcpyHostToDevice, s));
-        int rc = cw_step_render(&e->cfg, &e->st, e->d_actions, e->d_reward, e->d_done, e->d_obs, e->d_goal_obs, nullptr,
+        int rc = cw_step_render(&e->cfg, &e->st, act_src /* pinned: the caller's own buffer or our staging copy */, e->h_reward, e->h_done, e->d_obs, e->d_goal_obs, nullptr,
                                 e->d_stats, e->flags, s);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(e->h_reward, e->d_reward, n * 5, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     } else {
         int k = 0;

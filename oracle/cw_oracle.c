@@ -151,8 +151,15 @@ static int32_t step_one(const CwoConfig *cfg, uint8_t *g, const uint8_t *ig, uin
 /* render(state): ray.py:442-486 */
 static void render_one(const CwoConfig *cfg, const uint8_t *g, uint32_t agent, uint8_t *obs) {
     const int W = cfg->W, H = cfg->H, PW = 4 * W;
-    for (int y = 0; y < 4 * H; y++)
-        for (int x = 0; x < PW; x++) memcpy(obs + ((size_t)y * PW + x) * 3, LUT[g[(y >> 2) * W + (x >> 2)]], 3);  /* :477-479 */
+    const size_t rowb = (size_t)PW * 3;
+    for (int br = 0; br < H; br++) {                       /* colour LUT + x4 upsample, ray.py:477-479 */
+        uint8_t *row = obs + (size_t)(4 * br) * rowb;
+        for (int bc = 0; bc < W; bc++) {
+            const uint8_t *col = LUT[g[br * W + bc]];
+            for (int k = 0; k < 4; k++) memcpy(row + (size_t)(4 * bc + k) * 3, col, 3);
+        }
+        for (int k = 1; k < 4; k++) memcpy(row + k * rowb, row, rowb);   /* the 4 pixel rows of a cell row are equal */
+    }
     int r = agent & 0xFF, c = (agent >> 8) & 0xFF, h = (agent >> 16) & 0xFF;
     for (int y = 4 * r + 1; y < 4 * r + 3; y++)
         for (int x = 4 * c + 1; x < 4 * c + 3; x++) memset(obs + ((size_t)y * PW + x) * 3, 255, 3);              /* :483 */
