@@ -214,7 +214,8 @@ def run_ours(args):
         while N * frame_bytes * ring < 300e6 and ring < 64:
             ring *= 2
     env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=dev, auto_reset=True, obs_mode=wl["obs"],
-                                     env_id_base=rank * N, obs_buffers=ring)
+                                     env_id_base=rank * N, obs_buffers=ring, goal_images=not args.no_goal_images,
+                                     max_steps=args.max_steps)
     env.reset()
     if wl["dense"]:
         dense_worlds(env, torch, 99 + rank)
@@ -380,6 +381,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="shorter CPU baseline / e2e legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-goal-images", action="store_true", help="experiment: skip imagine_obs / goal + init frames")
+    ap.add_argument("--max-steps", type=int, default=300, help="experiment: episode length (reference default 300)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

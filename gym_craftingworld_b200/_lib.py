@@ -72,7 +72,7 @@ def load():
     """Build (if stale) and load libcw_b200.so; raises if that is impossible -- there is no CPU path."""
     global _lib
     if _lib is None:
-        path = _build.build()
+        path = os.environ.get("CW_LIB_PATH") or _build.build()     # CW_LIB_PATH: A/B experiments with another build
         if not os.path.exists(path):
             raise ImportError(f"gym_craftingworld_b200: CUDA library missing at {path}")
         lib = C.CDLL(path)

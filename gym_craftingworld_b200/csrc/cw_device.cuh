@@ -182,8 +182,14 @@ __device__ __forceinline__ void stats_add(const CwConfig& cfg, unsigned long lon
 // Writes grid + init_grid (global; and `sg` if non-null, a shared copy) and episode[n]; returns agent/goal.
 // `rng` is left positioned after the placement draws so imagine_warp can continue the same stream.
 // ------------------------------------------------------------------------------------------------------
+struct Sparse8 {   // a world with (at most) one object per entry: cell index + object code, static indexing only
+    uint32_t cell[8];
+    uint32_t code[8];
+};
+
 __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& st, int64_t n, uint8_t* sg, WarpPhilox& rng,
-                                           uint32_t& agent_out, uint32_t& goal_out) {
+                                           uint32_t& agent_out, uint32_t& goal_out, Sparse8* objs = nullptr,
+                                           uint32_t* s_scratch = nullptr) {
     const int lane = lane_id();
     const uint32_t ep = st.episode[n];
     rng.init(st.seed, st.env_id_base + (uint64_t)n, ep);
@@ -215,6 +221,22 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
             if (sg) reinterpret_cast<uint4*>(sg)[ch] = v4;
         }
         agent_new = st.fixed_agent[idx] & 0xFFFFu;
+        if (objs) {   // object list of the pooled world (one of each code): found by one pass over the tile
+            __syncwarp();
+            for (int ch = lane; ch < nchunk; ch += 32) {
+                const uint4 v4 = src[ch];
+                const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    const uint32_t c = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+                    if (c >= 1 && c <= 8) s_scratch[c - 1] = (uint32_t)(16 * ch + b);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; k++) { objs->cell[k] = s_scratch[k]; objs->code[k] = (uint32_t)(k + 1); }
+            __syncwarp();
+        }
     } else {
         // sample_state: 8 objects + agent on 9 distinct uniform cells (ray.py:605-613)
         const uint32_t ncell = (uint32_t)(cfg.H * cfg.W);
@@ -249,6 +271,10 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
         }
         const uint32_t ar = cells[8] / (uint32_t)cfg.W;
         agent_new = ar | ((cells[8] - ar * (uint32_t)cfg.W) << 8);
+        if (objs) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { objs->cell[k] = cells[k]; objs->code[k] = (uint32_t)(k + 1); }
+        }
     }
     if (lane == 0) st.episode[n] = ep + 1;
     agent_out = agent_new;                                                       // holding nothing
@@ -256,7 +282,66 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
     __syncwarp();
 }
 
-// warp-cooperative scans over a shared-memory grid, in np.where (row-major) order
+// warp-cooperative scans over a shared-memory grid tile, in np.where (row-major) order.
+// A lane owns one 16-byte chunk (16 cells) per pass: byte-SIMD compare (__vcmpeq4) -> 16-bit match mask, so a
+// 21x21 tile (28 chunks) is one pass.  Cells >= n (row padding) and the `skip` cell never match.
+__device__ __forceinline__ uint32_t match_mask16(const uint8_t* g, int chunk, int n, int code, int skip) {
+    const uint4 v = reinterpret_cast<const uint4*>(g)[chunk];
+    const uint32_t pat = (uint32_t)code * 0x01010101u;
+    auto nib = [&](uint32_t w) {   // byte-equality -> 4 bits (multiply gathers bits 0,8,16,24 into 24..27)
+        return ((((__vcmpeq4(w, pat) >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+    };
+    uint32_t m = nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
+    const int left = n - 16 * chunk;                     // valid cells in this chunk
+    if (left < 16) m &= left > 0 ? ((1u << left) - 1u) : 0u;
+    const int sk = skip - 16 * chunk;
+    if (sk >= 0 && sk < 16) m &= ~(1u << sk);
+    return m;
+}
+// position of the j-th (0-based) set bit of m; j < popc(m).  (__fns is software-emulated and slow.)
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int j) {
+    for (int i = 0; i < j; i++) m &= m - 1;
+    return __ffs(m) - 1;
+}
+#ifndef CW_SCAN_SIMD
+#define CW_SCAN_SIMD 0   // measured on B200: the plain 32-cells-per-pass loop is faster on this serial path (A/B, same box)
+#endif
+#if CW_SCAN_SIMD
+__device__ __forceinline__ int warp_count(const uint8_t* g, int n, int code, int skip) {
+    const int nchunk = (n + 15) >> 4;
+    int cnt = 0;
+    for (int base = 0; base < nchunk; base += 32) {
+        const int ch = base + lane_id();
+        cnt += ch < nchunk ? __popc(match_mask16(g, ch, n, code, skip)) : 0;
+    }
+    return (int)__reduce_add_sync(0xffffffffu, (unsigned)cnt);
+}
+__device__ __forceinline__ int warp_nth(const uint8_t* g, int n, int code, int k, int skip) {
+    const int nchunk = (n + 15) >> 4;
+    const int lane = lane_id();
+    for (int base = 0; base < nchunk; base += 32) {
+        const int ch = base + lane;
+        const uint32_t m = ch < nchunk ? match_mask16(g, ch, n, code, skip) : 0u;
+        const int c = __popc(m);
+        int incl = c;                                     // inclusive prefix sum over lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (k < total) {
+            const uint32_t hit = __ballot_sync(0xffffffffu, incl > k);
+            const int owner = __ffs(hit) - 1;
+            int pos = 0;
+            if (lane == owner) pos = nth_set_bit(m, k - (incl - c));
+            return __shfl_sync(0xffffffffu, 16 * ch + pos, owner);
+        }
+        k -= total;
+    }
+    return -1;
+}
+#else
 __device__ __forceinline__ int warp_count(const uint8_t* g, int n, int code, int skip) {
     int cnt = 0;
     for (int base = 0; base < n; base += 32) {
@@ -272,11 +357,12 @@ __device__ __forceinline__ int warp_nth(const uint8_t* g, int n, int code, int k
         const bool p = (i < n) && (g[i] == code) && (i != skip);
         const uint32_t m = __ballot_sync(0xffffffffu, p);
         const int c = __popc(m);
-        if (k < c) return base + (int)__fns(m, 0, k + 1);
+        if (k < c) return base + nth_set_bit(m, k);
         k -= c;
     }
     return -1;
 }
+#endif
 __device__ __forceinline__ void warp_set(uint8_t* g, int cell, int code) {
     __syncwarp();
     if (lane_id() == 0) g[cell] = (uint8_t)code;
@@ -362,6 +448,102 @@ __device__ __forceinline__ void imagine_warp(const CwConfig& cfg, uint8_t* g, ui
 }
 
 // ------------------------------------------------------------------------------------------------------
+// imagine_obs (ray.py:220-299) in closed form for a world FRESH from reset(): sample_state / the fixed pool put
+// exactly one of each object on the grid and the agent on an empty cell, so the world is an 8-entry list
+// (index k = object k+1 initially) and every "np.where" candidate set of the reference has at most two
+// members with known indices.  Same draws, same order, same results as imagine_warp's grid scans (the oracle
+// checks both); ~10x fewer dependent instructions, which matters because it runs on one warp per reset.
+// Row-major (np.where) order of two objects = order of their cell indices.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nth_free_cell(const Sparse8& o, uint32_t extra, uint32_t spot) {
+    // spot-th (0-based) cell, in row-major order, that holds no object and is not `extra`:
+    // least fixed point of c = spot + #{occupied <= c}
+    uint32_t c = spot;
+    for (;;) {
+        uint32_t cnt = extra <= c ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) cnt += (o.code[k] != 0 && o.cell[k] <= c) ? 1u : 0u;
+        const uint32_t nx = spot + cnt;
+        if (nx == c) return c;
+        c = nx;
+    }
+}
+__device__ __forceinline__ uint32_t count_objects(const Sparse8& o) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) n += o.code[k] != 0 ? 1u : 0u;
+    return n;
+}
+
+__device__ __forceinline__ void imagine_fresh(const CwConfig& cfg, Sparse8& o, uint32_t& agent, uint32_t des, WarpPhilox& rng) {
+    enum { S = 0, A = 1, HM = 2, R = 3, T = 4, B = 5, HO = 6, WH = 7 };   // list index of each initial object
+    const uint32_t HW = (uint32_t)(cfg.H * cfg.W), W = (uint32_t)cfg.W;
+    const uint32_t acell = (agent & 0xFF) * W + ((agent >> 8) & 0xFF);
+    uint32_t anew = acell;
+    if ((des >> T_MAKE_BREAD) & 1u) o.code[WH] = BREAD;                             // ray.py:226-231
+    if ((des >> T_EAT_BREAD) & 1u) {                                                // ray.py:232-237
+        const bool two = o.code[WH] == BREAD;                                       // breads: B, and WH once baked
+        const uint32_t k = rng.uniform(two ? 2u : 1u);
+        const bool b_first = !two || o.cell[B] < o.cell[WH];
+        if ((k == 0) == b_first) o.code[B] = EMPTY; else o.code[WH] = EMPTY;
+    }
+    if ((des >> T_CHOP_TREE) & 1u) o.code[T] = STICKS;                              // ray.py:238-243
+    if ((des >> T_MOVE_STICKS) & 1u) {                                              // ray.py:244-257
+        const bool two = o.code[T] == STICKS;                                       // sticks: S, and T once chopped
+        const uint32_t k = rng.uniform(two ? 2u : 1u);
+        const bool s_first = !two || o.cell[S] < o.cell[T];
+        const bool move_s = (k == 0) == s_first;
+        const uint32_t fr = HW - count_objects(o) - 1u;                             // [:9]: the agent cell is occupied
+        if ((int)fr > 0) {
+            const uint32_t dst = nth_free_cell(o, acell, rng.uniform(fr));
+            if (move_s) o.cell[S] = dst; else o.cell[T] = dst;
+        }
+    }
+    if ((des >> T_BUILD_HOUSE) & 1u) {                                              // ray.py:258-264
+        const bool two = o.code[T] == STICKS;
+        const uint32_t k = rng.uniform(two ? 2u : 1u);
+        const bool s_first = !two || o.cell[S] < o.cell[T];
+        if ((k == 0) == s_first) o.code[S] = HOUSE; else o.code[T] = HOUSE;
+    }
+    if ((des >> T_CHOP_ROCK) & 1u) o.code[R] = EMPTY;                               // ray.py:265-268
+    if ((des >> T_GO_TO_HOUSE) & 1u) {                                              // ray.py:269-276
+        const bool s_house = o.code[S] == HOUSE, t_house = o.code[T] == HOUSE;      // at most one of them was built
+        const bool two = s_house || t_house;
+        const uint32_t other = s_house ? o.cell[S] : o.cell[T];
+        const uint32_t k = rng.uniform(two ? 2u : 1u);
+        const bool ho_first = !two || o.cell[HO] < other;
+        anew = ((k == 0) == ho_first) ? o.cell[HO] : other;
+    }
+    if ((des >> T_MOVE_AXE) & 1u) {                                                 // ray.py:277-286
+        const uint32_t fr = HW - count_objects(o);                                  // [:8]: the agent cell is allowed
+        if ((int)fr > 0) o.cell[A] = nth_free_cell(o, 0xFFFFFFFFu, rng.uniform(fr));
+    }
+    if ((des >> T_MOVE_HAMMER) & 1u) {                                              // ray.py:287-297
+        const uint32_t fr = HW - count_objects(o);
+        if ((int)fr > 0) o.cell[HM] = nth_free_cell(o, 0xFFFFFFFFu, rng.uniform(fr));
+    }
+    const uint32_t ar = anew / W;
+    agent = (agent & 0xFFFF0000u) | ar | ((anew - ar * W) << 8);
+}
+
+// grid tile (16-byte chunks, one per lane per pass) from an object list
+__device__ __forceinline__ void tile_from_objects(const Sparse8& o, int nchunk, uint8_t* tile) {
+    for (int ch = lane_id(); ch < nchunk; ch += 32) {
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if ((int)(o.cell[k] >> 4) == ch && o.code[k] != 0) {
+                const uint32_t v = o.code[k] << (8 * (o.cell[k] & 3));
+                const int wi = (o.cell[k] >> 2) & 3;
+                w0 |= wi == 0 ? v : 0; w1 |= wi == 1 ? v : 0; w2 |= wi == 2 ? v : 0; w3 |= wi == 3 ? v : 0;
+            }
+        }
+        reinterpret_cast<uint4*>(tile)[ch] = make_uint4(w0, w1, w2, w3);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
 // render(state): ray.py:442-486.  Expands `nbands` cell rows starting at `band0` of the shared-memory grid `sg`
 // into the shared-memory frame chunk `frame` (uint32 words; a pixel row is 3*W words = 12 bytes per cell).
 // A thread owns one cell: colour LUT -> the three 32-bit words of its 4-pixel RGB span -> 4 pixel rows; the
@@ -370,14 +552,14 @@ __device__ __forceinline__ void imagine_warp(const CwConfig& cfg, uint8_t* g, ui
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void compose_bands(const CwConfig& cfg, const uint8_t* __restrict__ sg, uint32_t agent,
                                               int band0, int nbands, uint32_t* __restrict__ frame,
-                                              const uint32_t* __restrict__ slut, uint32_t w_magic) {
+                                              const uint32_t* __restrict__ slut, uint32_t w_magic, int ctid, int cthreads) {
     const int W = cfg.W, roww = 3 * W;
     const int ar = agent & 0xFF, ac = (agent >> 8) & 0xFF, ah = (agent >> 16) & 0xFF;
     const int acell = ar * W + ac - band0 * W;
     const uint32_t hc = ah ? slut[ah] : 0x00FFFFFFu;
     const int ncells = nbands * W;
     const uint8_t* src = sg + band0 * W;
-    for (int i = threadIdx.x; i < ncells; i += blockDim.x) {
+    for (int i = ctid; i < ncells; i += cthreads) {
         const int b = (int)__umulhi((uint32_t)i, w_magic);   // i / W
         const int col = i - b * W;
         const uint32_t rgb = slut[src[i]];
@@ -419,6 +601,10 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+// ---- named barriers (producer arrives, consumers sync; `count` = all participating threads) ----------------
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // ---- programmatic dependent launch (sm_90+) -------------------------------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

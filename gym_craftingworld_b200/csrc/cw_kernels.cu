@@ -39,21 +39,35 @@ struct EnvArgs {
     uint32_t w_magic;        // floor(2^32 / W) + 1
 };
 
-enum : int { FL_RENDER = 1, FL_FRESH = 2, FL_GOAL = 4 };
+#ifdef CW_TIMING
+__device__ unsigned long long* g_dbg = nullptr;   // [CTA][16] globaltimer stamps (experiments only)
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CW_STAMP(slot) do { if (g_dbg && (threadIdx.x == 0 || (slot) >= 8) ) g_dbg[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+#else
+#define CW_STAMP(slot) do { } while (0)
+#endif
+
+enum : int { FL_RENDER = 1, FL_FRESH = 2, FL_GOAL = 4, FL_PENDING = 8 /* reset warp has work on this world */ };
+constexpr int kComposeThreads = 128;   // warps 0..3 expand frames (warp 0 also steps the group)
+constexpr int kEnvThreads = 160;       // + warp 4: the reset warp
+enum : int { BAR_COMPOSE = 1, BAR_RESET_DONE = 2 };
 
 // One CTA iteration handles a GROUP of G consecutive worlds:
 //   A  grid tiles of the group arrive in shared memory (cp.async, prefetched one group ahead; scalars are
 //      prefetched into registers of warp 0, lane i = world i of the group)
-//   B  warp 0 steps the G worlds lane-parallel on the shared tiles, then re-seeds finished / forced worlds
-//      cooperatively (Philox reset + imagine_obs into a scratch tile)
-//   C  all 4 warps expand one world at a time into a ring of F frame slots; thread 0 streams each slot out with
-//      a TMA bulk store and only waits for the store issued F-1 slots earlier, so composing overlaps the stores.
+//   B  warp 0 steps the G worlds lane-parallel on the shared tiles and publishes per-world flags
+//   R  warp 4 (the reset warp) re-seeds finished / forced worlds -- Philox reset + imagine_obs into a scratch
+//      tile: ~2.5k dependent instructions on one warp -- WHILE
+//   C  warps 0..3 expand the other worlds one at a time into a ring of F frame slots; thread 0 streams each slot
+//      out with a TMA bulk store and only waits for the store issued F-1 slots earlier, so composing overlaps
+//      the stores.  Worlds the reset warp worked on are emitted last, after its named-barrier arrival.
 // dynamic shared memory: [tiles 2 x G x cell_stride][imagine scratch G x cell_stride][ring F x chunk_bytes]
-__global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
+__global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_lut[9];
-    __shared__ uint32_t s_agent[32], s_gagent[32];
+    __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32];
     __shared__ uint32_t s_flag[32];
+    __shared__ uint32_t s_obj[8];
 
     const int H = cfg.H, W = cfg.W, cs = cfg.cell_stride;
     const int G = args.group, F = args.nbuf, mode = args.mode;
@@ -64,6 +78,7 @@ __global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, cons
     uint8_t* simag = smem + 2 * G * cs;
     uint8_t* ring = smem + 3 * G * cs;
     const int tid = threadIdx.x;
+    const bool composer = tid < kComposeThreads;
     const int nchunk16 = cs >> 4;
     const uint8_t* grid_in = args.rgrid ? args.rgrid : st.grid;
     const uint32_t* agent_in = args.ragent ? args.ragent : st.agent;
@@ -71,9 +86,11 @@ __global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, cons
 
     // Programmatic dependent launch: let the next launch in the stream start its prologue now, and do not touch
     // anything the previous launch wrote (state, frames) until it has fully completed.
+    CW_STAMP(0);
     pdl_launch_dependents();
     if (tid < 9) s_lut[tid] = kColorLUT[tid];
     pdl_wait();
+    CW_STAMP(1);
 
     // tile + scalar prefetch of group `g` (tiles -> stage `sgi`; scalars -> registers of warp 0)
     uint32_t p_agent = 0, p_goal = 0;
@@ -84,7 +101,7 @@ __global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, cons
             const int cnt = (int)min((int64_t)G, st.n - e0);
             const uint8_t* src = grid_in + e0 * cs;
             uint8_t* dst = tiles + (size_t)sgi * G * cs;
-            for (int i = tid; i < cnt * nchunk16; i += blockDim.x) cp_async16(dst + 16 * i, src + 16 * i);
+            for (int i = tid; i < cnt * nchunk16; i += kEnvThreads) cp_async16(dst + 16 * i, src + 16 * i);
             if (tid < cnt) {
                 const int64_t e = e0 + tid;
                 p_agent = agent_in[e];
@@ -96,23 +113,21 @@ __global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, cons
         cp_async_commit();
     };
 
-    uint32_t q = 0;                                               // frame-chunk sequence number (ring slot = q % F)
-    int slot = 0;
-    // expand one world (tile `src`) into the ring and stream it to dst (and dst2 when non-null)
+    int slot = 0;                                                 // ring slot of the next frame chunk
+    // expand one world (tile `src`) into the ring and stream it to dst (and dst2 when non-null); compose warps only
     auto emit_frame = [&](const uint8_t* src, uint32_t ag, uint8_t* dst, uint8_t* dst2) {
         for (int band0 = 0; band0 < H; band0 += args.bands_per_chunk) {
             const int nb = min(args.bands_per_chunk, H - band0);
             uint8_t* fb = ring + (size_t)slot * chunk_bytes;
-            compose_bands(cfg, src, ag, band0, nb, reinterpret_cast<uint32_t*>(fb), s_lut, args.w_magic);
+            compose_bands(cfg, src, ag, band0, nb, reinterpret_cast<uint32_t*>(fb), s_lut, args.w_magic, tid, kComposeThreads);
             fence_proxy_async_smem();
             if (tid == 0) bulk_wait_read_dyn(F - 2);              // frees the slot the NEXT chunk composes into
-            __syncthreads();
+            bar_sync(BAR_COMPOSE, kComposeThreads);
             if (tid == 0) {
                 bulk_store(dst + (size_t)band0 * band_bytes, fb, band_bytes * nb);
                 if (dst2) bulk_store(dst2 + (size_t)band0 * band_bytes, fb, band_bytes * nb);
                 bulk_commit();
             }
-            q++;
             slot = (slot + 1 == F) ? 0 : slot + 1;
         }
     };
@@ -126,19 +141,20 @@ __global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, cons
         prefetch(gi + gridDim.x, stage ^ 1);
         cp_async_wait<1>();                                       // everything but the newest group has landed
         __syncthreads();
+        CW_STAMP(2);
         uint8_t* gt = tiles + (size_t)stage * G * cs;             // this group's tiles
         const int64_t e0 = gi * G;
-        // ---- B: warp 0 steps the group lane-parallel, then re-seeds worlds cooperatively ----------------------
+        // ---- B: warp 0 steps the group lane-parallel -------------------------------------------------------------
         if (tid < 32) {
             const int lane = tid;
             const int64_t e = e0 + lane;
             const bool valid = lane < G && e < st.n;
             uint32_t agent = c_agent, goal = c_goal, flag = 0;
-            bool do_reset = false;
             if (valid) {
                 const bool skip = (mode & M_FORCE_RESET) && !c_forced;   // masked reset: untouched worlds are skipped
                 if (!skip && (mode & M_RENDER)) flag |= FL_RENDER;
-                do_reset = (mode & M_FORCE_RESET) && c_forced;
+                if ((mode & M_FORCE_RESET) && c_forced) flag |= FL_PENDING;
+                if (mode & M_IMAGINE_ONLY) flag |= FL_PENDING;
                 if (mode & M_STEP) {
                     int t = c_t, wcell, wval;
                     bool dn;
@@ -147,67 +163,86 @@ __global__ void __launch_bounds__(128, 4) cw_env_kernel(const CwConfig cfg, cons
                     args.reward[e] = rew;
                     args.done[e] = dn ? 1 : 0;
                     if (dn && (mode & M_AUTO_RESET)) {
-                        do_reset = true;
+                        flag |= FL_PENDING;
                         if (args.stats) stats_add(cfg, args.stats, goal, t, rew);
                     } else {
                         st.agent[e] = agent; st.goal[e] = goal; st.t[e] = t;
                     }
                 }
             }
-            uint32_t m = __ballot_sync(0xffffffffu, valid && do_reset);
-            while (m) {                                           // reset(): ray.py:156-218, one world at a time
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const int64_t er = e0 + src;
+            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; }
+        }
+        __syncthreads();
+        CW_STAMP(3);
+        if (!composer) {
+            // ---- R: the reset warp works through the pending worlds, then arrives on BAR_RESET_DONE -----------------
+            const int lane = tid - kComposeThreads;
+            for (int i = 0; i < G; i++) {
+                uint32_t flag = s_flag[i];
+                if (!(flag & FL_PENDING)) continue;
+                const int64_t er = e0 + i;
+                uint8_t* tile = gt + i * cs;
                 WarpPhilox rng;
-                uint32_t ag, gl;
-                reset_warp(cfg, st, er, gt + src * cs, rng, ag, gl);
-                if (lane == src) { agent = ag; goal = gl; st.agent[er] = ag; st.goal[er] = gl; st.t[er] = 0; flag |= FL_FRESH; }
-                if (args.goal_obs) {                              // desired_goal = imagine_obs(): ray.py:191, 220-299
-                    uint8_t* im = simag + src * cs;
+                uint32_t ag = s_agent[i], gl = s_goal[i];
+                if (!(mode & M_IMAGINE_ONLY)) {                   // reset(): ray.py:156-218
+                    Sparse8 objs;
+                    reset_warp(cfg, st, er, tile, rng, ag, gl, &objs, s_obj);
+                    if (lane == 0) { st.agent[er] = ag; st.goal[er] = gl; st.t[er] = 0; s_agent[i] = ag; }
+                    flag |= FL_FRESH;
+                    if (args.goal_obs) {                          // desired_goal = imagine_obs(): ray.py:191, 220-299
+                        uint32_t gag = ag;
+                        imagine_fresh(cfg, objs, gag, gl >> 16, rng);      // closed form on the 8-object list
+                        tile_from_objects(objs, nchunk16, simag + i * cs);
+                        if (lane == 0) s_gagent[i] = gag;
+                        flag |= FL_GOAL;
+                    }
+                } else {                                          // cw_imagine: arbitrary (dense) injected state
+                    rng.init(st.seed, st.env_id_base + (uint64_t)er, st.episode[er]);
+                    uint8_t* im = simag + i * cs;
                     for (int ch = lane; ch < nchunk16; ch += 32)
-                        reinterpret_cast<uint4*>(im)[ch] = reinterpret_cast<const uint4*>(gt + src * cs)[ch];
+                        reinterpret_cast<uint4*>(im)[ch] = reinterpret_cast<const uint4*>(tile)[ch];
                     __syncwarp();
                     uint32_t gag = ag;
                     imagine_warp(cfg, im, gag, gl >> 16, rng);
-                    if (lane == src) { s_gagent[src] = gag; flag |= FL_GOAL; }
+                    if (lane == 0) s_gagent[i] = gag;
+                    flag |= FL_GOAL;
                 }
+                if (lane == 0) s_flag[i] = flag;
+                __syncwarp();
             }
-            if (mode & M_IMAGINE_ONLY) {                          // goal frame of the current (injected) state
-                m = __ballot_sync(0xffffffffu, valid);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int64_t er = e0 + src;
-                    WarpPhilox rng;
-                    rng.init(st.seed, st.env_id_base + (uint64_t)er, st.episode[er]);
-                    uint8_t* im = simag + src * cs;
-                    for (int ch = lane; ch < nchunk16; ch += 32)
-                        reinterpret_cast<uint4*>(im)[ch] = reinterpret_cast<const uint4*>(gt + src * cs)[ch];
-                    __syncwarp();
-                    uint32_t gag = __shfl_sync(0xffffffffu, agent, src);
-                    const uint32_t gl = __shfl_sync(0xffffffffu, goal, src);
-                    imagine_warp(cfg, im, gag, gl >> 16, rng);
-                    if (lane == src) { s_gagent[src] = gag; flag |= FL_GOAL; }
-                }
+            __threadfence_block();                                // tiles / s_* written above are visible to the composers
+#ifdef CW_TIMING
+            if (tid == kComposeThreads && g_dbg) { int np = 0; for (int i = 0; i < G; i++) np += (s_flag[i] & FL_PENDING) ? 1 : 0; g_dbg[(size_t)blockIdx.x * 16 + 9] = np; }
+#endif
+            if (tid == kComposeThreads) CW_STAMP(8);
+            bar_arrive(BAR_RESET_DONE, kEnvThreads);
+        } else {
+            // ---- C: expand + stream out: untouched worlds first, worlds from the reset warp after its arrival ------
+            for (int i = 0; i < G; i++) {
+                const uint32_t flag = s_flag[i];
+                if (!(flag & FL_RENDER) || (flag & FL_PENDING)) continue;
+                const size_t off = (size_t)(e0 + i) * frame_bytes;
+                emit_frame(gt + i * cs, s_agent[i], args.obs + off, nullptr);
             }
-            if (lane < G) { s_agent[lane] = agent; s_flag[lane] = valid ? flag : 0; }
+            CW_STAMP(4);
+            bar_sync(BAR_RESET_DONE, kEnvThreads);
+            CW_STAMP(5);
+            for (int i = 0; i < G; i++) {
+                const uint32_t flag = s_flag[i];
+                if (!(flag & FL_PENDING)) continue;
+                const size_t off = (size_t)(e0 + i) * frame_bytes;
+                if (flag & FL_GOAL) emit_frame(simag + i * cs, s_gagent[i], args.goal_obs + off, nullptr);
+                if (flag & FL_RENDER)
+                    emit_frame(gt + i * cs, s_agent[i], args.obs + off, ((flag & FL_FRESH) && args.init_obs) ? args.init_obs + off : nullptr);
+            }
         }
-        __syncthreads();
-        // ---- C: expand + stream out, one world at a time -----------------------------------------------------
-        for (int i = 0; i < G; i++) {
-            const uint32_t flag = s_flag[i];
-            if (!flag) continue;
-            const size_t off = (size_t)(e0 + i) * frame_bytes;
-            if (flag & FL_GOAL) emit_frame(simag + i * cs, s_gagent[i], args.goal_obs + off, nullptr);
-            if (flag & FL_RENDER)
-                emit_frame(gt + i * cs, s_agent[i], args.obs + off, ((flag & FL_FRESH) && args.init_obs) ? args.init_obs + off : nullptr);
-        }
+        CW_STAMP(6);
         __syncthreads();                                          // tiles / s_* of this stage are rewritten next
         stage ^= 1;
     }
     cp_async_wait<0>();
     if (tid == 0) bulk_wait_all();
+    CW_STAMP(7);
 }
 
 // one thread per world, K steps per launch (K = 1: cw_step; K > 1: cw_rollout)
@@ -383,7 +418,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
         for (int i = 0; i < dev->n_occ; i++)
             if (dev->occ[i].smem == smem) per_sm = dev->occ[i].per_sm;
         if (per_sm == 0) {
-            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEnvThreads, smem);
             if (e != cudaSuccess) return (int)e;
             if (per_sm < 1) per_sm = 1;
             if (dev->n_occ < 64) { dev->occ[dev->n_occ].smem = smem; dev->occ[dev->n_occ].per_sm = per_sm; dev->n_occ++; }
@@ -401,7 +436,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     int64_t blocks = (int64_t)dev->sms * best_per_sm;
     const int64_t groups = (st->n + bestG - 1) / bestG;
     if (blocks > groups) blocks = groups;
-    cudaError_t le = launch_pdl(kern, dim3((unsigned)blocks), dim3(128), smem, stream, *cfg, *st, args);
+    cudaError_t le = launch_pdl(kern, dim3((unsigned)blocks), dim3(kEnvThreads), smem, stream, *cfg, *st, args);
     return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
 
@@ -412,6 +447,10 @@ using namespace cw;
 extern "C" {
 
 int cw_abi_version(void) { return CW_ABI_VERSION; }
+
+#ifdef CW_TIMING
+int cw_debug_set_timing(void* dev_ptr) { return (int)cudaMemcpyToSymbol(cw::g_dbg, &dev_ptr, sizeof(void*)); }
+#endif
 
 const char* cw_error_string(int code) {
     switch (code) {
