@@ -550,6 +550,25 @@ __device__ __forceinline__ void tile_from_objects(const Sparse8& o, int nchunk, 
 // owner of the agent cell patches rows 1,2 itself (2x2 white block :483, bottom row = held colour :484-486),
 // so no second pass / barrier is needed.  Lanes hit consecutive cells => word stride 3 => conflict-free STS.
 // ------------------------------------------------------------------------------------------------------
+#ifndef CW_COMPOSE_BANDWISE
+#define CW_COMPOSE_BANDWISE 0
+#endif
+__device__ __forceinline__ void compose_cell(const uint8_t* __restrict__ src, int i, int b, int col, int roww, int acell,
+                                             uint32_t hc, uint32_t* __restrict__ frame, const uint32_t* __restrict__ slut) {
+    const uint32_t rgb = slut[src[i]];
+    const uint32_t w0 = __byte_perm(rgb, 0, 0x0210), w1 = __byte_perm(rgb, 0, 0x1021), w2 = __byte_perm(rgb, 0, 0x2102);
+    uint32_t* p = frame + b * (4 * roww) + 3 * col;
+    p[0] = w0; p[1] = w1; p[2] = w2;
+    p[roww + 0] = w0; p[roww + 1] = w1; p[roww + 2] = w2;
+    p[2 * roww + 0] = w0; p[2 * roww + 1] = w1; p[2 * roww + 2] = w2;
+    p[3 * roww + 0] = w0; p[3 * roww + 1] = w1; p[3 * roww + 2] = w2;
+    if (i == acell) {                                          // one thread per frame: agent overlay (ray.py:483-486)
+        p[roww + 0] = w0 | 0xFF000000u; p[roww + 1] = 0xFFFFFFFFu; p[roww + 2] = w2 | 0x000000FFu;
+        p[2 * roww + 0] = __byte_perm(w0, hc, 0x4210);
+        p[2 * roww + 1] = __byte_perm(hc, 0, 0x1021);
+        p[2 * roww + 2] = __byte_perm(w2, hc, 0x3216);
+    }
+}
 __device__ __forceinline__ void compose_bands(const CwConfig& cfg, const uint8_t* __restrict__ sg, uint32_t agent,
                                               int band0, int nbands, uint32_t* __restrict__ frame,
                                               const uint32_t* __restrict__ slut, uint32_t w_magic, int ctid, int cthreads) {
@@ -557,25 +576,19 @@ __device__ __forceinline__ void compose_bands(const CwConfig& cfg, const uint8_t
     const int ar = agent & 0xFF, ac = (agent >> 8) & 0xFF, ah = (agent >> 16) & 0xFF;
     const int acell = ar * W + ac - band0 * W;
     const uint32_t hc = ah ? slut[ah] : 0x00FFFFFFu;
-    const int ncells = nbands * W;
     const uint8_t* src = sg + band0 * W;
+#if CW_COMPOSE_BANDWISE
+    // one band (cell row) per warp pass: lanes = columns, so a warp-wide STS never straddles a band boundary
+    const int lane = ctid & 31, warp = ctid >> 5, nwarps = cthreads >> 5;
+    for (int b = warp; b < nbands; b += nwarps)
+        for (int col = lane; col < W; col += 32) compose_cell(src, b * W + col, b, col, roww, acell, hc, frame, slut);
+#else
+    const int ncells = nbands * W;
     for (int i = ctid; i < ncells; i += cthreads) {
         const int b = (int)__umulhi((uint32_t)i, w_magic);   // i / W
-        const int col = i - b * W;
-        const uint32_t rgb = slut[src[i]];
-        const uint32_t w0 = __byte_perm(rgb, 0, 0x0210), w1 = __byte_perm(rgb, 0, 0x1021), w2 = __byte_perm(rgb, 0, 0x2102);
-        uint32_t* p = frame + b * (4 * roww) + 3 * col;
-        p[0] = w0; p[1] = w1; p[2] = w2;
-        p[roww + 0] = w0; p[roww + 1] = w1; p[roww + 2] = w2;
-        p[2 * roww + 0] = w0; p[2 * roww + 1] = w1; p[2 * roww + 2] = w2;
-        p[3 * roww + 0] = w0; p[3 * roww + 1] = w1; p[3 * roww + 2] = w2;
-        if (i == acell) {                                      // one thread per frame: agent overlay (ray.py:483-486)
-            p[roww + 0] = w0 | 0xFF000000u; p[roww + 1] = 0xFFFFFFFFu; p[roww + 2] = w2 | 0x000000FFu;
-            p[2 * roww + 0] = __byte_perm(w0, hc, 0x4210);
-            p[2 * roww + 1] = __byte_perm(hc, 0, 0x1021);
-            p[2 * roww + 2] = __byte_perm(w2, hc, 0x3216);
-        }
+        compose_cell(src, i, b, i - b * W, roww, acell, hc, frame, slut);
     }
+#endif
 }
 
 // ---- TMA bulk store (shared::cta -> global), sm_90+ : SASS UBLKCP ---------------------------------------
