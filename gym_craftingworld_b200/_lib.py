@@ -30,7 +30,7 @@ class CwState(C.Structure):
     _fields_ = [("grid", C.c_void_p), ("init_grid", C.c_void_p), ("agent", C.c_void_p), ("goal", C.c_void_p),
                 ("t", C.c_void_p), ("episode", C.c_void_p), ("n", C.c_int64), ("seed", C.c_uint64),
                 ("env_id_base", C.c_uint64), ("fixed_grid", C.c_void_p), ("fixed_agent", C.c_void_p),
-                ("n_fixed", C.c_int64)]
+                ("n_fixed", C.c_int64), ("goal_grid", C.c_void_p), ("goal_agent", C.c_void_p), ("init_agent", C.c_void_p)]
 
 
 class CwError(RuntimeError):

@@ -189,12 +189,18 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     reset_warp(cfg, st, er, tile, rng, ag, gl, &objs, s_obj);
                     if (lane == 0) { st.agent[er] = ag; st.goal[er] = gl; st.t[er] = 0; s_agent[i] = ag; }
                     flag |= FL_FRESH;
-                    if (args.goal_obs) {                          // desired_goal = imagine_obs(): ray.py:191, 220-299
+                    if (lane == 0 && st.init_agent) st.init_agent[er] = ag;
+                    if (args.goal_obs || st.goal_grid) {          // desired_goal = imagine_obs(): ray.py:191, 220-299
                         uint32_t gag = ag;
                         imagine_fresh(cfg, objs, gag, gl >> 16, rng);      // closed form on the 8-object list
                         tile_from_objects(objs, nchunk16, simag + i * cs);
+                        if (st.goal_grid) {                       // compact goal state (one-hot observation family)
+                            for (int ch = lane; ch < nchunk16; ch += 32)
+                                reinterpret_cast<uint4*>(st.goal_grid + er * cs)[ch] = reinterpret_cast<const uint4*>(simag + i * cs)[ch];
+                            if (lane == 0) st.goal_agent[er] = gag;
+                        }
                         if (lane == 0) s_gagent[i] = gag;
-                        flag |= FL_GOAL;
+                        if (args.goal_obs) flag |= FL_GOAL;
                     }
                 } else {                                          // cw_imagine: arbitrary (dense) injected state
                     rng.init(st.seed, st.env_id_base + (uint64_t)er, st.episode[er]);
@@ -204,8 +210,13 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     __syncwarp();
                     uint32_t gag = ag;
                     imagine_warp(cfg, im, gag, gl >> 16, rng);
+                    if (st.goal_grid) {
+                        for (int ch = lane; ch < nchunk16; ch += 32)
+                            reinterpret_cast<uint4*>(st.goal_grid + er * cs)[ch] = reinterpret_cast<const uint4*>(im)[ch];
+                        if (lane == 0) st.goal_agent[er] = gag;
+                    }
                     if (lane == 0) s_gagent[i] = gag;
-                    flag |= FL_GOAL;
+                    if (args.goal_obs) flag |= FL_GOAL;
                 }
                 if (lane == 0) s_flag[i] = flag;
                 __syncwarp();
@@ -468,6 +479,7 @@ static int check_state(const CwState* st) {
     if (st->n < 0) return CW_E_BADCONFIG;
     if (st->n > 0 && (!st->grid || !st->init_grid || !st->agent || !st->goal || !st->t || !st->episode)) return CW_E_NULLPTR;
     if (st->n_fixed < 0 || (st->n_fixed > 0 && (!st->fixed_grid || !st->fixed_agent))) return CW_E_NULLPTR;
+    if (st->goal_grid && !st->goal_agent) return CW_E_NULLPTR;
     return 0;
 }
 
@@ -523,11 +535,12 @@ int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* action
     if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
     if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
     if (st->n == 0) return 0;
-    if (!actions || !reward || !done || !obs) return CW_E_NULLPTR;
+    if (!actions || !reward || !done) return CW_E_NULLPTR;
+    if (!obs && (goal_obs || init_obs)) return CW_E_NULLPTR;
     EnvArgs a = {};
     a.actions = actions; a.reward = reward; a.done = done; a.obs = obs; a.goal_obs = goal_obs; a.init_obs = init_obs;
     a.stats = (unsigned long long*)stats;
-    a.mode = M_STEP | M_RENDER | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
+    a.mode = M_STEP | (obs ? M_RENDER : 0) | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
     return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
 }
 
@@ -535,7 +548,7 @@ int cw_imagine(const CwConfig* cfg, const CwState* st, uint8_t* goal_obs, void* 
     int rc = check_config(cfg); if (rc) return rc;
     rc = check_state(st); if (rc) return rc;
     if (st->n == 0) return 0;
-    if (!goal_obs) return CW_E_NULLPTR;
+    if (!goal_obs && !st->goal_grid) return CW_E_NULLPTR;
     EnvArgs a = {};
     a.goal_obs = goal_obs; a.mode = M_IMAGINE_ONLY;
     return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);

@@ -96,6 +96,37 @@ class GoalInfo(Mapping):
         return len(self._KEYS)
 
 
+class OneHotObs(Mapping):
+    """Observation dict of the one-hot family (``carftingworld_onehot.py:203, 310, 369-371``): values are expanded from
+    the compact device state on first access after each step/reset (``achieved_goal is observation``, as upstream)."""
+    _KEYS = ("observation", "desired_goal", "achieved_goal", "init_observation")
+
+    def __init__(self, env):
+        self._env, self._version, self._cache = env, env._obs_version, {}
+
+    def __getitem__(self, k):
+        env = self._env
+        if self._version != env._obs_version:
+            self._version, self._cache = env._obs_version, {}
+        key = "observation" if k == "achieved_goal" else k
+        if key not in self._KEYS:
+            raise KeyError(k)
+        if key not in self._cache:
+            if key == "observation":
+                self._cache[key] = env.onehot()
+            elif key == "desired_goal":
+                self._cache[key] = env.onehot(grid=env.goal_grid, agent=env.goal_agent)
+            else:
+                self._cache[key] = env.onehot(grid=env.init_grid, agent=env.init_agent)
+        return self._cache[key]
+
+    def __iter__(self):
+        return iter(self._KEYS)
+
+    def __len__(self):
+        return len(self._KEYS)
+
+
 class BatchedCraftingWorldEnv:
     """N independent CraftingWorld worlds on one GPU behind the reference's Env surface."""
 
@@ -108,8 +139,8 @@ class BatchedCraftingWorldEnv:
         if store_gif:
             raise NotImplementedError("GIF recording (ray.py:565-597, 769-782) is a host-side debugging side channel; "
                                       "out of scope (DESIGN.md)")
-        if obs_mode not in ("pixels", "compact"):
-            raise ValueError("obs_mode must be 'pixels' or 'compact'")
+        if obs_mode not in ("pixels", "compact", "onehot"):
+            raise ValueError("obs_mode must be 'pixels', 'compact' or 'onehot'")
         self.num_envs = int(num_envs)
         if self.num_envs < 1:
             raise ValueError("num_envs must be >= 1")
@@ -166,6 +197,12 @@ class BatchedCraftingWorldEnv:
             if self.goal_images:
                 self.desired_goal = torch.zeros(self.frame_shape, dtype=torch.uint8, device=dev)
                 self.init_obs = torch.zeros(self.frame_shape, dtype=torch.uint8, device=dev)
+        self.goal_grid = self.goal_agent = self.init_agent = None
+        if obs_mode == "onehot":                  # compact imagined goal state + INIT agent word (one-hot family)
+            self.goal_grid = torch.zeros((N, stride), dtype=torch.uint8, device=dev)
+            self.goal_agent = torch.zeros(N, dtype=torch.int32, device=dev)
+            self.init_agent = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._obs_version = 0
         self._fixed_grid = self._fixed_agent = None
         self._seed = None
         self._state = _lib.CwState()
@@ -194,6 +231,7 @@ class BatchedCraftingWorldEnv:
             s.fixed_grid, s.fixed_agent, s.n_fixed = self._fixed_grid.data_ptr(), self._fixed_agent.data_ptr(), self.fixed_init_state
         else:
             s.fixed_grid, s.fixed_agent, s.n_fixed = None, None, 0
+        s.goal_grid, s.goal_agent, s.init_agent = self._ptr(self.goal_grid), self._ptr(self.goal_agent), self._ptr(self.init_agent)
 
     def _generate_fixed_states(self, n):
         """``generate_fixed_states`` (``ray.py:149-154``): pre-sample ``n`` worlds with ``sample_state``."""
@@ -205,6 +243,7 @@ class BatchedCraftingWorldEnv:
         pool.grid, pool.init_grid, pool.agent, pool.goal = g.data_ptr(), ig.data_ptr(), ag.data_ptr(), gl.data_ptr()
         pool.t, pool.episode, pool.n, pool.seed, pool.env_id_base = t.data_ptr(), ep.data_ptr(), n, self._seed, FIXED_POOL_ID_BASE
         pool.n_fixed = 0
+        pool.goal_grid = pool.goal_agent = pool.init_agent = None
         with torch.cuda.device(self.device):
             _lib.check(self._lib.cw_reset(C.byref(self.cfg), C.byref(pool), None, None, None, None, self._stream()), "cw_reset(pool)")
         self._fixed_grid, self._fixed_agent = g, ag
@@ -253,12 +292,14 @@ class BatchedCraftingWorldEnv:
         H, W = self.cfg.H, self.cfg.W
         return self.grid[:, :H * W].view(self.num_envs, H, W)
 
-    def onehot(self, init=False):
-        """One-hot ``uint8[N, H, W, 12]`` state (``obs_one_hot`` / ``INIT_OBS_VECTOR``, ``ray.py:605-613, 183``)."""
+    def onehot(self, init=False, grid=None, agent=None):
+        """One-hot ``uint8[N, H, W, 12]`` state (``obs_one_hot`` / ``INIT_OBS_VECTOR``, ``ray.py:605-613, 183``) of the
+        current worlds, or of the given compact ``grid uint8[N, cell_stride]`` / ``agent int32[N]`` tensors."""
         out = torch.empty((self.num_envs, self.cfg.H, self.cfg.W, 12), dtype=torch.uint8, device=self.device)
-        src = self.init_grid if init else self.grid
+        src = grid if grid is not None else (self.init_grid if init else self.grid)
+        ag = agent if agent is not None else self.agent
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.cw_onehot(C.byref(self.cfg), src.data_ptr(), self.agent.data_ptr(), out.data_ptr(),
+            _lib.check(self._lib.cw_onehot(C.byref(self.cfg), src.data_ptr(), ag.data_ptr(), out.data_ptr(),
                                            self.num_envs, self._stream()), "cw_onehot")
         return out
 
@@ -274,6 +315,8 @@ class BatchedCraftingWorldEnv:
         if self.obs_mode == "pixels":
             return {"observation": self.obs, "desired_goal": self.desired_goal, "achieved_goal": self.obs,
                     "init_observation": self.init_obs}                                      # ray.py:194-196
+        if self.obs_mode == "onehot":
+            return OneHotObs(self)
         return {"observation": self.grid_view, "agent": self.agent, "desired_goal": self.desired_mask,
                 "achieved_goal": self.achieved_mask, "init_observation": self.init_grid}
 
@@ -296,6 +339,7 @@ class BatchedCraftingWorldEnv:
             _lib.check(self._lib.cw_reset(C.byref(self.cfg), C.byref(self._state), self._ptr(m), self._ptr(self.obs),
                                           self._ptr(self.desired_goal), self._ptr(self.init_obs), self._stream()), "cw_reset")
         self._is_reset = True
+        self._obs_version += 1
         return self._observation()
 
     def _as_actions(self, actions):
@@ -325,10 +369,14 @@ class BatchedCraftingWorldEnv:
                 rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
                                               self._done_u8.data_ptr(), self.obs.data_ptr(), self._ptr(self.desired_goal),
                                               self._ptr(self.init_obs), self.stats.data_ptr(), flags, self._stream())
+            elif self.obs_mode == "onehot":       # no pixels, but resets must produce the imagined goal state
+                rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                                              self._done_u8.data_ptr(), None, None, None, self.stats.data_ptr(), flags, self._stream())
             else:
                 rc = self._lib.cw_step(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
                                        self._done_u8.data_ptr(), self.stats.data_ptr(), flags, self._stream())
         _lib.check(rc, "cw_step")
+        self._obs_version += 1
         return self._observation(), self.reward, self.done, self._info
 
     def rollout(self, actions, return_trace=True):
@@ -423,7 +471,12 @@ class BatchedCraftingWorldEnv:
                 with torch.cuda.device(self.device):
                     _lib.check(self._lib.cw_imagine(C.byref(self.cfg), C.byref(self._state), self.desired_goal.data_ptr(),
                                                     self._stream()), "cw_imagine")
+        elif self.obs_mode == "onehot":
+            self.init_agent.copy_(self.agent)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.cw_imagine(C.byref(self.cfg), C.byref(self._state), None, self._stream()), "cw_imagine")
         self._is_reset = True
+        self._obs_version += 1
         return self._observation()
 
     def export_state(self):
@@ -446,3 +499,35 @@ class BatchedCraftingWorldEnv:
 
     def close(self):
         pass
+
+
+class BatchedCraftingWorldEnvFlat(BatchedCraftingWorldEnv):
+    """Batched mirror of ``CraftingWorldEnvFlat`` (``craftingworld_flat.py:40-57, 119, 185``): identical dynamics,
+    8x8 grid / 100 steps by default, no ``fixed_init_state``, and ``reset``/``step`` return the bare image tensor."""
+
+    def __init__(self, num_envs, size=(8, 8), max_steps=100, store_gif=False, render_save_rate=1, task_list=TASK_LIST,
+                 selected_tasks=TASK_LIST, number_of_tasks=None, stacking=True, reward_style=None, **kw):
+        kw.setdefault("goal_images", False)
+        super().__init__(num_envs, size=size, fixed_init_state=0, max_steps=max_steps, store_gif=store_gif,
+                         render_save_rate=render_save_rate, task_list=task_list, selected_tasks=selected_tasks,
+                         number_of_tasks=number_of_tasks, stacking=stacking, reward_style=reward_style, obs_mode="pixels", **kw)
+        self.observation_space = spaces.Box(0, 255, (4 * self.cfg.W, 4 * self.cfg.H, 3), np.uint8)   # flat.py:57
+
+    def reset(self, mask=None):
+        return super().reset(mask)["observation"]                                          # flat.py:119
+
+    def step(self, actions):
+        obs, reward, done, info = super().step(actions)
+        return obs["observation"], reward, done, info                                      # flat.py:185
+
+
+class BatchedCraftingWorldEnvOneHot(BatchedCraftingWorldEnv):
+    """Batched mirror of ``CraftingWorldEnvOneHot`` (``carftingworld_onehot.py``): the observation is the one-hot state
+    ``uint8[N, H, W, 12]`` (no rendering), ``desired_goal`` the imagined one-hot state (``:310``)."""
+
+    def __init__(self, num_envs, *args, **kw):
+        kw["obs_mode"] = "onehot"
+        super().__init__(num_envs, *args, **kw)
+        vec = self.observation_vector_space["observation"]
+        self.observation_space = spaces.Dict(dict(observation=vec, desired_goal=vec, achieved_goal=vec,
+                                                  init_observation=vec))                   # onehot.py:84-103

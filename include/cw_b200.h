@@ -80,6 +80,12 @@ typedef struct CwState {
     const uint8_t* fixed_grid;   /* uint8 [n_fixed][cell_stride], nullable */
     const uint32_t* fixed_agent; /* uint32[n_fixed] */
     int64_t n_fixed;
+    /* optional compact outputs of reset() for the one-hot observation family (CraftingWorldEnvOneHot,
+     * carftingworld_onehot.py:203, 310): the imagined goal STATE and the agent word of INIT_OBS. Nullable; written by
+     * cw_reset / cw_step_render for every world they (re)seed. */
+    uint8_t* goal_grid;   /* uint8 [N][cell_stride]: imagine_obs final_state, object codes */
+    uint32_t* goal_agent; /* uint32[N]: agent word of the imagined state */
+    uint32_t* init_agent; /* uint32[N]: agent word at reset (INIT_OBS_VECTOR's agent channel) */
 } CwState;
 
 int cw_abi_version(void);
@@ -105,7 +111,8 @@ int cw_render(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, u
 
 /* step + (auto-reset) + render fused in one launch: what one reference `obs, r, d, info = env.step(a)` does
  * (ray.py:301-378 incl. render_edit 358), for N worlds.  goal_obs / init_obs (nullable) are rewritten only for
- * worlds that auto-reset in this call (desired_goal and init_observation of the new episode, ray.py:191-196). */
+ * worlds that auto-reset in this call (desired_goal and init_observation of the new episode, ray.py:191-196).
+ * obs may be NULL (no pixels: step + auto-reset + the compact goal outputs of CwState only). */
 int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
                    uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, void* stream);
 

@@ -1,0 +1,88 @@
+"""GPU (-m gpu): the observation-format adapters of SURVEY 8(f)-2 -- batched mirrors of CraftingWorldEnvFlat
+(craftingworld_flat.py) and CraftingWorldEnvOneHot (carftingworld_onehot.py) -- against golden traces / the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import compact, native, ref_shim
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cw():
+    import gym_craftingworld_b200 as pkg
+    assert torch.cuda.is_available()
+    return pkg
+
+
+def test_flat_env_defaults_and_trace(cw):
+    env = cw.BatchedCraftingWorldEnvFlat(4, seed=0)
+    assert (env.STATE_W, env.STATE_H, env.MAX_STEPS) == (8, 8, 100)            # craftingworld_flat.py:40-43
+    assert env.observation_space.shape == (32, 32, 3)
+    obs = env.reset()
+    assert isinstance(obs, torch.Tensor) and obs.shape == (4, 32, 32, 3)       # bare image, flat.py:119
+    d = gu.load("dense_8x8.npz")
+    B, T = d["actions"].shape
+    env = cw.BatchedCraftingWorldEnvFlat(B, size=(8, 8), max_steps=d["max_steps"], seed=0, auto_reset=False)
+    env.load_state(d["grid0"], d["r0"], d["c0"], d["hold0"], d["desired"])
+    for t in range(T):
+        obs, reward, done, info = env.step(d["actions"][:, t])
+        assert isinstance(obs, torch.Tensor)
+        assert np.array_equal(reward.cpu().numpy(), d["reward"][:, t]) and np.array_equal(done.cpu().numpy(), d["done"][:, t].astype(bool))
+        assert [gu.crc(f) for f in obs.cpu().numpy()] == list(d["frame_crc"][:, t]), t
+    assert set(info) == {"task_success", "desired_goal", "achieved_goal"}
+
+
+def test_onehot_env_matches_oracle(cw):
+    N, size, seed, K = 96, 6, 31, 40
+    env = cw.BatchedCraftingWorldEnvOneHot(N, size=(size, size), max_steps=9, seed=seed)
+    assert env.observation_space["observation"].shape == (size, size, 12)     # carftingworld_onehot.py:84-103
+    cfg = native.make_config(H=size, W=size, max_steps=9)
+    ob = native.OracleBatch(cfg, N, seed=seed)
+    pc = compact.Config(H=size, W=size, max_steps=9)
+
+    def onehot_of(grid, agent):
+        return np.stack([ref_shim.compact_to_onehot(grid[n, :size * size].reshape(size, size), int(agent[n] & 0xFF),
+                                                    int((agent[n] >> 8) & 0xFF), int((agent[n] >> 16) & 0xFF)) for n in range(N)]).astype(np.uint8)
+
+    def goal_of(episodes):
+        out = []
+        for n in range(N):
+            _, (g, r, c, h) = compact.reset_env(seed, n, int(episodes[n]) - 1, pc, with_goal=True)
+            out.append(ref_shim.compact_to_onehot(g, r, c, h))
+        return np.stack(out).astype(np.uint8)
+
+    obs = env.reset()
+    ob.reset()
+    assert obs["achieved_goal"] is obs["observation"]
+    assert np.array_equal(obs["observation"].cpu().numpy(), onehot_of(ob.grid, ob.agent))
+    assert np.array_equal(obs["init_observation"].cpu().numpy(), onehot_of(ob.grid, ob.agent))   # INIT_OBS copy, onehot.py:203
+    assert np.array_equal(obs["desired_goal"].cpu().numpy(), goal_of(ob.episode))             # imagined state, onehot.py:310
+    rng = np.random.RandomState(3)
+    init_grid, init_agent = ob.grid.copy(), ob.agent.copy()
+    for k in range(K):
+        a = rng.randint(0, 6, N).astype(np.uint8)
+        obs, reward, done, _ = env.step(a)
+        o_reward, o_done = ob.step_full(a, auto_reset=True)
+        fresh = o_done == 1
+        init_grid[fresh], init_agent[fresh] = ob.grid[fresh], ob.agent[fresh]
+        assert np.array_equal(reward.cpu().numpy(), o_reward) and np.array_equal(done.cpu().numpy(), fresh)
+        assert np.array_equal(obs["observation"].cpu().numpy(), onehot_of(ob.grid, ob.agent)), k
+        if k % 8 == 0 or k == K - 1:
+            assert np.array_equal(obs["desired_goal"].cpu().numpy(), goal_of(ob.episode)), k
+            assert np.array_equal(obs["init_observation"].cpu().numpy(), onehot_of(init_grid, init_agent)), k
+    assert ob.stats[0] > 0 and np.array_equal(env.stats.cpu().numpy(), ob.stats)
+
+
+def test_onehot_goal_state_renders_to_goal_frame(cw):
+    """The compact goal state of the one-hot family and the pixel goal frame are the same imagined world."""
+    N, seed = 200, 5
+    a = cw.BatchedCraftingWorldEnvOneHot(N, seed=seed)
+    b = cw.BatchedCraftingWorldEnv(N, seed=seed)
+    a.reset(); b.reset()
+    H, W = a.cfg.H, a.cfg.W
+    ag = a.goal_agent
+    frames = b.render(state=(a.goal_grid[:, :H * W].reshape(N, H, W), ag & 0xFF, (ag >> 8) & 0xFF, (ag >> 16) & 0xFF))
+    assert torch.equal(frames, b.desired_goal)
