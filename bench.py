@@ -9,8 +9,9 @@ sharded over ranks by global id with no data-path collective (weak scaling: per-
 24 x int64 episode-statistics vector is all-reduced over NCCL every 128 steps on a side stream.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (actions already in HBM, frames left in HBM);
-`e2e` is the same metric through the host-buffer C entry points (cw_host_step: pinned host actions -> device ->
-fused launches -> frames, reward, done back to pinned host memory); `roofline` is the fused kernel's algorithmic
+`e2e` is the same metric through the host-buffer C entry points (cw_host_step: actions from pinned host memory in,
+reward + done back to pinned host memory every step, frames produced in HBM; `e2e.frames_to_host` also copies every
+frame to the host and is PCIe-bound); `roofline` is the fused kernel's algorithmic
 bytes per launch / its mean launch duration against the measured HBM copy bandwidth; `cpu_baseline` times the CPU
 port of the reference's env loop on this box's host cores.  `--impl reference` times only that CPU port.
 """
@@ -372,7 +373,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=51200)
+    ap.add_argument("--steps", type=int, default=25600)
     ap.add_argument("--warmup", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
