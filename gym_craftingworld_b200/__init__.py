@@ -8,10 +8,11 @@ from . import _lib
 _lib.load()   # fail loudly at import time
 
 from .env import (ACTION_NAMES, COLORS_N, MAX_STEPS, OBJECTS, PICKUPABLE, TASK_LIST,  # noqa: E402
-                  BatchedCraftingWorldEnv, BatchedCraftingWorldEnvFlat, BatchedCraftingWorldEnvOneHot, make_config)
+                  BatchedCraftingWorldEnv, BatchedCraftingWorldEnvFlat, BatchedCraftingWorldEnvOneHot,
+                  BatchedCraftingWorldEnvAltObs, make_config)
 from .host_env import HostCraftingWorldEnv  # noqa: E402
 from .dist import StatsReducer, shard_range  # noqa: E402
 
-__all__ = ["BatchedCraftingWorldEnv", "BatchedCraftingWorldEnvFlat", "BatchedCraftingWorldEnvOneHot", "HostCraftingWorldEnv", "StatsReducer", "shard_range", "make_config", "TASK_LIST",
+__all__ = ["BatchedCraftingWorldEnv", "BatchedCraftingWorldEnvFlat", "BatchedCraftingWorldEnvOneHot", "BatchedCraftingWorldEnvAltObs", "HostCraftingWorldEnv", "StatsReducer", "shard_range", "make_config", "TASK_LIST",
            "OBJECTS", "PICKUPABLE", "ACTION_NAMES", "COLORS_N", "MAX_STEPS"]
 __version__ = "0.1.0"

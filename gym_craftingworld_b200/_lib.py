@@ -16,7 +16,7 @@ F_AUTO_RESET = 1
 
 # every symbol include/cw_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_rollout",
-           "cw_imagine", "cw_onehot", "cw_host_create", "cw_host_reset", "cw_host_step", "cw_host_stats",
+           "cw_imagine", "cw_onehot", "cw_render_alt", "cw_host_create", "cw_host_reset", "cw_host_step", "cw_host_stats",
            "cw_host_device_state", "cw_host_destroy"]
 
 
@@ -55,6 +55,7 @@ def _declare(lib):
         "cw_rollout": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
         "cw_imagine": [cfgp, stp, vp, vp],
         "cw_onehot": [cfgp, vp, vp, vp, i64, vp],
+        "cw_render_alt": [cfgp, vp, vp, vp, i64, vp],
         "cw_host_create": [cfgp, i64, ci, u64, u64, ci, C.POINTER(vp)],
         "cw_host_reset": [vp, vp, vp],
         "cw_host_step": [vp, vp, vp, vp, vp],

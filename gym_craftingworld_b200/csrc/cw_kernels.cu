@@ -321,6 +321,37 @@ __global__ void __launch_bounds__(256) cw_onehot_kernel(const CwConfig cfg, cons
     }
 }
 
+// AltObs renderer (craftingworld_altobs.py:489-548): one thread per output pixel (3 x int16)
+__device__ __constant__ int16_t kCPV[9][3] = {{45, 82, 160},  {255, 102, 102}, {204, 204, 0},   {211, 211, 211}, {34, 133, 34},
+                                              {0, 215, 255},  {153, 52, 255},  {10, 215, 100},  {0, 0, 255}};   // altobs.py:26-27
+__global__ void __launch_bounds__(256) cw_render_alt_kernel(const CwConfig cfg, const uint8_t* __restrict__ grid,
+                                                            const uint32_t* __restrict__ agent, int16_t* __restrict__ out,
+                                                            int64_t n_pixels) {
+    const int H = cfg.H, W = cfg.W, PW = 3 * W, P = (3 * H + 3) * PW;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_pixels; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t env = idx / P;
+        const int p = (int)(idx - env * P);
+        const int y = p / PW, x = p - y * PW;
+        const uint32_t ag = agent[env];
+        const int ar = ag & 0xFF, ac = (ag >> 8) & 0xFF, h = (ag >> 16) & 0xFF;
+        int16_t v0 = 0, v1 = 0, v2 = 0;
+        if (y >= 3 * H) {                                          // status strip, altobs.py:542-545
+            if (h != 0 && x >= 3 && x < 6) { v0 = 255; v1 = 255; v2 = 255; }
+        } else {
+            const int r = y / 3, c = x / 3, k = (y - 3 * r) * 3 + (x - 3 * c);      // sub-pixel k of cell (r,c), altobs.py:45-51
+            const int code = grid[env * cfg.cell_stride + r * W + c];
+            int m = (k < 8 && code == k + 1) ? 1 : 0;              // object channels
+            if (r == ar && c == ac) {
+                if (k == 8) m = 1;                                 // agent channel
+                if (h != 0 && k == h - 1) m += 1;                  // held item added onto channels 0..2, altobs.py:531-533
+            }
+            v0 = (int16_t)(m * kCPV[k][0]); v1 = (int16_t)(m * kCPV[k][1]); v2 = (int16_t)(m * kCPV[k][2]);
+        }
+        int16_t* o = out + idx * 3;
+        o[0] = v0; o[1] = v1; o[2] = v2;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
@@ -566,6 +597,21 @@ int cw_onehot(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, u
     const int64_t cap = (int64_t)dev->sms * 16;
     if (blocks > cap) blocks = cap;
     cw_onehot_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, grid, agent, (uint32_t*)onehot, n_words, 0);
+    return (int)cudaGetLastError();
+}
+
+int cw_render_alt(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, int16_t* obs, int64_t n, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    if (n < 0) return CW_E_BADCONFIG;
+    if (n == 0) return 0;
+    if (!grid || !agent || !obs) return CW_E_NULLPTR;
+    DeviceInfo* dev;
+    rc = device_info(&dev); if (rc) return rc;
+    const int64_t n_pixels = n * (3 * cfg->H + 3) * 3 * cfg->W;
+    int64_t blocks = (n_pixels + 255) / 256;
+    const int64_t cap = (int64_t)dev->sms * 16;
+    if (blocks > cap) blocks = cap;
+    cw_render_alt_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, grid, agent, obs, n_pixels);
     return (int)cudaGetLastError();
 }
 

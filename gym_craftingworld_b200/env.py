@@ -531,3 +531,67 @@ class BatchedCraftingWorldEnvOneHot(BatchedCraftingWorldEnv):
         vec = self.observation_vector_space["observation"]
         self.observation_space = spaces.Dict(dict(observation=vec, desired_goal=vec, achieved_goal=vec,
                                                   init_observation=vec))                   # onehot.py:84-103
+
+
+class AltObs(Mapping):
+    """Observation dict of the AltObs variant: int16 frames rendered lazily from the compact device state."""
+    _KEYS = ("observation", "desired_goal", "achieved_goal", "init_observation")
+
+    def __init__(self, env):
+        self._env, self._version, self._cache = env, env._obs_version, {}
+
+    def __getitem__(self, k):
+        env = self._env
+        if self._version != env._obs_version:
+            self._version, self._cache = env._obs_version, {}
+        key = "observation" if k == "achieved_goal" else k
+        if key not in self._KEYS:
+            raise KeyError(k)
+        if key not in self._cache:
+            if key == "observation":
+                self._cache[key] = env.render_alt(env.grid, env.agent)
+            elif key == "desired_goal":
+                self._cache[key] = env.render_alt(env.goal_grid, env.goal_agent)
+            else:
+                self._cache[key] = env.render_alt(env.init_grid, env.init_agent)
+        return self._cache[key]
+
+    def __iter__(self):
+        return iter(self._KEYS)
+
+    def __len__(self):
+        return len(self._KEYS)
+
+
+class BatchedCraftingWorldEnvAltObs(BatchedCraftingWorldEnv):
+    """Batched mirror of ``CraftingWorldEnvAltObs`` (``craftingworld_altobs.py``; unregistered upstream): the dynamics
+    of ``CraftingWorldEnvRay`` with the 3x3-sub-pixel renderer (``:489-548``).  Frames are ``int16[N, 3H+3, 3W, 3]``
+    because pixel values reach 510 upstream; ``stacked_obs=True`` returns the four frames stacked on axis 1
+    (``:116-119, 258-259, 408-410``)."""
+
+    def __init__(self, num_envs, *args, stacked_obs=False, **kw):
+        kw["obs_mode"] = "onehot"                      # compact goal / init state; frames are rendered from it
+        super().__init__(num_envs, *args, **kw)
+        self.stacked_obs = stacked_obs is True
+        pw, ph = (self.cfg.W + 1) * 3, self.cfg.H * 3                                      # altobs.py:115
+        img = spaces.Box(0, 255, (pw, ph, 3), np.int16)
+        self.observation_space = (spaces.Box(0, 255, (4, pw, ph, 3), np.int16) if self.stacked_obs else
+                                  spaces.Dict(dict(observation=img, desired_goal=img, achieved_goal=img, init_observation=img)))
+
+    def render_alt(self, grid, agent):
+        out = torch.empty((self.num_envs, 3 * self.cfg.H + 3, 3 * self.cfg.W, 3), dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cw_render_alt(C.byref(self.cfg), grid.data_ptr(), agent.data_ptr(), out.data_ptr(), self.num_envs,
+                                               self._stream()), "cw_render_alt")
+        return out
+
+    def _observation(self):
+        obs = AltObs(self)
+        if self.stacked_obs:
+            return torch.stack([obs["observation"], obs["desired_goal"], obs["achieved_goal"], obs["init_observation"]], dim=1)
+        return obs
+
+    def render(self, state=None, mode="Non", tile_size=4):
+        if state is not None:
+            raise NotImplementedError("AltObs render of foreign states: use render_alt(grid, agent)")
+        return self.render_alt(self.grid, self.agent)

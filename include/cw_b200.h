@@ -130,6 +130,12 @@ int cw_imagine(const CwConfig* cfg, const CwState* st, uint8_t* goal_obs, void* 
 int cw_onehot(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, uint8_t* onehot, int64_t n,
               void* stream);
 
+/* AltObs renderer (craftingworld_altobs.py:489-548, unregistered upstream): int16[N][3H+3][3W][3]; 3x3 sub-pixels per
+ * cell, sub-pixel k lit with CPV_COLORS[k] x multiplicity of channel k (a held item adds to channels 0..2 at the agent
+ * cell, so values reach 510 -- hence int16), plus a 3-row status strip (255 at columns 3..5 while holding). */
+int cw_render_alt(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, int16_t* obs, int64_t n,
+                  void* stream);
+
 /* ---- host-buffer API: the env behind an opaque handle, all arguments HOST pointers ----------------------
  * The drop-in for a host-language caller without device memory of its own: the library owns the device state,
  * pinned staging buffers and streams; each call copies actions host->device, runs the fused launch(es) in

@@ -169,6 +169,31 @@ def render(grid, r, c, hold):
     return img
 
 
+# AltObs renderer (craftingworld_altobs.py:26-27, 45-51, 489-548): 3x3 sub-pixels per cell, sub-pixel k (row-major)
+# lit with CPV_COLORS[k] times the multiplicity of channel k (objects 0..7, agent 8; a held item adds 1 to
+# channel 0..2 at the agent cell, so values reach 2 x 255 -> int16), plus a 3-row status strip at the bottom.
+CPV = np.array([(45, 82, 160), (255, 102, 102), (204, 204, 0), (211, 211, 211), (34, 133, 34), (0, 215, 255),
+                (153, 52, 255), (10, 215, 100), (0, 0, 255)], dtype=np.int16)                # altobs.py:26-27
+
+
+def render_alt(grid, r, c, hold):
+    """``int16[3H+3, 3W, 3]`` AltObs frame of one world (``craftingworld_altobs.py:489-548``)."""
+    grid = np.asarray(grid)
+    H, W = grid.shape
+    m = np.zeros((H, W, 9), np.int16)
+    for k in range(8):
+        m[:, :, k] = grid == k + 1                                              # objects_new[..., :8]
+    m[r, c, 8] = 1                                                              # agent channel
+    if hold:
+        m[r, c, hold - 1] += 1                                                  # holding_new added onto channels 0..2 (:531-533)
+    img = np.zeros((3 * H + 3, 3 * W, 3), np.int16)
+    for k in range(9):                                                          # OBJECT_ENCODING_M / COLORS_A_M (:45-51, :540-541)
+        img[k // 3:3 * H:3, k % 3::3] = m[:, :, k, None] * CPV[k]
+    if hold:
+        img[3 * H:, 3:6] = 255                                                  # :543-545
+    return img
+
+
 # ----------------------------------------------------------------------------------------------------
 # Philox4x32-10 counter-based stream (D. E. Shaw Research "Random123"; Salmon et al., SC'11)
 # ----------------------------------------------------------------------------------------------------

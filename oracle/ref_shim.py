@@ -114,6 +114,13 @@ def load_reference():
     return ray
 
 
+def load_reference_altobs():
+    """The reference's ``craftingworld_altobs`` module (unregistered AltObs variant)."""
+    load_reference()
+    import gym_craftingworld.envs.craftingworld_altobs as alt  # noqa: E402
+    return alt
+
+
 # ----------------------------------------------------------------------------------------------------
 # converters: reference one-hot int[H,W,12]  <->  compact state (SURVEY.md Appendix A.1 / B.2 / B.3)
 # ----------------------------------------------------------------------------------------------------

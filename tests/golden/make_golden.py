@@ -184,7 +184,28 @@ def gen_quirks(name):
         run_batch(os.path.join(HERE, nm), H, W, worlds, np.asarray(scripts), 12, subset, list(range(16)))
 
 
+def gen_altobs(name, src="dense_8x8.npz", stride=6):
+    """AltObs frames (craftingworld_altobs.py render, int values up to 510) of the states along an existing trace:
+    the reference AltObs env is injected with each state and asked for render(state)."""
+    alt = ref_shim.load_reference_altobs()
+    d = np.load(os.path.join(HERE, src))
+    H, W = int(d["H"]), int(d["W"])
+    env = alt.CraftingWorldEnvAltObs(size=(W, H))
+    B, T = d["actions"].shape
+    ts = list(range(0, T, stride))
+    frames = np.zeros((B, len(ts), 3 * H + 3, 3 * W, 3), np.int16)
+    for b in range(B):
+        for i, t in enumerate(ts):
+            st = ref_shim.compact_to_onehot(d["grid"][b, t], int(d["r"][b, t]), int(d["c"][b, t]), int(d["hold"][b, t]))
+            frames[b, i] = env.render(st)
+    np.savez_compressed(os.path.join(HERE, name), src=src, frame_t=np.asarray(ts, np.int32), frames=frames)
+    print(f"{name}: {frames.shape} max pixel {frames.max()}")
+
+
 if __name__ == "__main__":
+    if "--altobs-only" in sys.argv:
+        gen_altobs("altobs_8x8.npz")
+        sys.exit(0)
     gen_quirks("quirks_5x5.npz")
     gen_cfg1("cfg1_21x21.npz")
     gen_sampled("sampled_21x21.npz", 21, 21, 48, 320, 7, 300, 40)
@@ -193,3 +214,4 @@ if __name__ == "__main__":
     gen_dense("dense_8x8.npz", 8, 8, 96, 96, 13, 80, False, 4)
     gen_dense("dense_21x21.npz", 21, 21, 64, 160, 14, 120, False, 32)
     gen_dense("dense_32x32.npz", 32, 32, 32, 160, 15, 150, False, 40)
+    gen_altobs("altobs_8x8.npz")

@@ -9,7 +9,14 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_files():
-    return sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Step/render traces (the AltObs frame file has its own layout and loader)."""
+    return sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(p).startswith("altobs"))
+
+
+def load_altobs(name="altobs_8x8.npz"):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    return str(z["src"]), z["frame_t"], z["frames"]
 
 
 def load(name):

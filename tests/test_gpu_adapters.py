@@ -86,3 +86,40 @@ def test_onehot_goal_state_renders_to_goal_frame(cw):
     ag = a.goal_agent
     frames = b.render(state=(a.goal_grid[:, :H * W].reshape(N, H, W), ag & 0xFF, (ag >> 8) & 0xFF, (ag >> 16) & 0xFF))
     assert torch.equal(frames, b.desired_goal)
+
+
+def test_altobs_env_matches_reference_frames_and_oracle(cw):
+    """cw_render_alt against frames frozen from the reference AltObs renderer, then the AltObs env end to end."""
+    src, frame_t, frames = gu.load_altobs()
+    d = gu.load(src)
+    B = frames.shape[0]
+    env = cw.BatchedCraftingWorldEnvAltObs(B, size=(8, 8), max_steps=d["max_steps"], seed=0, auto_reset=False)
+    for i, t in enumerate(frame_t):
+        env.load_state(d["grid"][:, t], d["r"][:, t], d["c"][:, t], d["hold"][:, t], d["desired"])
+        got = env.observation["observation"].cpu().numpy()
+        assert got.dtype == np.int16 and np.array_equal(got, frames[:, i]), t
+    assert frames.max() > 255
+    # end to end with auto-reset: observation / init / goal frames from the oracle's compact states
+    N, seed = 64, 12
+    env = cw.BatchedCraftingWorldEnvAltObs(N, size=(6, 6), max_steps=8, seed=seed)
+    ob = native.OracleBatch(native.make_config(H=6, W=6, max_steps=8), N, seed=seed)
+    pc = compact.Config(H=6, W=6, max_steps=8)
+    obs = env.reset(); ob.reset()
+
+    def frames_of(grid, agent):
+        return np.stack([compact.render_alt(grid[n, :36].reshape(6, 6), int(agent[n] & 0xFF), int((agent[n] >> 8) & 0xFF),
+                                            int((agent[n] >> 16) & 0xFF)) for n in range(N)])
+    rng = np.random.RandomState(0)
+    for k in range(30):
+        a = rng.randint(0, 6, N).astype(np.uint8)
+        obs, reward, done, _ = env.step(a)
+        o_reward, o_done = ob.step_full(a, auto_reset=True)
+        assert np.array_equal(reward.cpu().numpy(), o_reward)
+        assert np.array_equal(obs["observation"].cpu().numpy(), frames_of(ob.grid, ob.agent)), k
+    goal = []
+    for n in range(N):
+        _, (g, r, c, h) = compact.reset_env(seed, n, int(ob.episode[n]) - 1, pc, with_goal=True)
+        goal.append(compact.render_alt(g, r, c, h))
+    assert np.array_equal(obs["desired_goal"].cpu().numpy(), np.stack(goal))
+    stacked = cw.BatchedCraftingWorldEnvAltObs(4, size=(6, 6), seed=1, stacked_obs=True)
+    assert stacked.reset().shape == (4, 4, 21, 18, 3)
