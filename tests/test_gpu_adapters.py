@@ -123,3 +123,19 @@ def test_altobs_env_matches_reference_frames_and_oracle(cw):
     assert np.array_equal(obs["desired_goal"].cpu().numpy(), np.stack(goal))
     stacked = cw.BatchedCraftingWorldEnvAltObs(4, size=(6, 6), seed=1, stacked_obs=True)
     assert stacked.reset().shape == (4, 4, 21, 18, 3)
+
+
+def test_vector_env_facade(cw):
+    venv = cw.CraftingWorldVectorEnv(32, size=(5, 5), max_steps=6, seed=3)
+    obs, info = venv.reset(seed=3)
+    assert obs["observation"].shape == (32, 20, 20, 3) and info == {}
+    seen_trunc = False
+    for k in range(12):
+        obs, reward, terminated, truncated, info = venv.step(torch.randint(0, 6, (32,), device="cuda", dtype=torch.uint8))
+        assert not bool((terminated & truncated).any())
+        assert bool(((reward == 6) == terminated).all())
+        seen_trunc |= bool(truncated.any())
+    assert seen_trunc and set(info) == {"achieved_mask", "desired_mask"}
+    nv = cw.CraftingWorldVectorEnv(8, to_numpy=True, size=(5, 5), seed=0)
+    o, _ = nv.reset()
+    assert isinstance(o["observation"], np.ndarray)

@@ -84,3 +84,19 @@ def test_spaces_metadata():
     b = spaces.Box(0, 255, (84, 84, 3), np.uint8)
     assert b.shape == (84, 84, 3) and b.low == 0 and b.high == 255
     assert spaces.Dict({"a": b})["a"] is b
+
+
+def test_gif_recorder_writes_episode_gifs(tmp_path):
+    """Host-side GIF dump (the role of allow_gif_storage, ray.py:565-597, 769-782) on synthetic frames."""
+    from PIL import Image
+    rec = cw.GifRecorder(index=1, directory=str(tmp_path), env_id=7, scale=2)
+    rng = np.random.RandomState(0)
+    for t in range(6):
+        frames = rng.randint(0, 255, (3, 20, 20, 3)).astype(np.uint8)
+        done = np.array([False, t == 4, False])
+        rec.capture({"observation": frames}, done)
+    # auto-reset semantics: the frame returned WITH done is already the next episode's first frame
+    assert len(rec.saved) == 1 and rec.saved[0].endswith("E0(3).gif") and len(rec.frames) == 2
+    with Image.open(rec.saved[0]) as im:
+        assert im.n_frames == 4 and im.size == (40, 40)
+    assert cw.register_envs() == []                       # neither gym nor gymnasium is installed here
