@@ -222,7 +222,7 @@ def run_ours(args):
         dense_worlds(env, torch, 99 + rank)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     tape = torch.randint(0, 6, (TAPE, N), generator=gen, device=dev, dtype=torch.uint8)
-    reducer = cw.StatsReducer(env.stats, every=TAPE) if world > 1 else None
+    reducer = cw.StatsReducer(env.stats, every=TAPE, inline=os.environ.get("CW_STATS_INLINE", "0") == "1") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -340,7 +340,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base,
             "episode_stats_rank0": {k: stats_local[k] for k in ("episodes", "successes", "mean_return", "mean_length")},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -367,7 +367,28 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything else (NCCL banners, library chatter) was
+    redirected to stderr by quiet_stdout()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout() -> None:
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
@@ -385,6 +406,7 @@ def main():
     ap.add_argument("--no-goal-images", action="store_true", help="experiment: skip imagine_obs / goal + init frames")
     ap.add_argument("--max-steps", type=int, default=300, help="experiment: episode length (reference default 300)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -21,8 +21,10 @@ def shard_range(total: int, rank: int, world: int):
 class StatsReducer:
     """Periodic all-reduce of ``env.stats`` (backend-agnostic: NCCL on GPUs, gloo in the CPU tests)."""
 
-    def __init__(self, stats: torch.Tensor, every: int = 128, group=None):
-        self.stats, self.every, self.group = stats, int(every), group
+    def __init__(self, stats: torch.Tensor, every: int = 128, group=None, inline: bool = False):
+        """``inline=True`` issues the all-reduce on the caller's stream instead of a side stream (it then costs its
+        ~20-30 us latency once per ``every`` steps but never competes with the env kernel for SM slots)."""
+        self.stats, self.every, self.group, self.inline = stats, int(every), group, bool(inline)
         self.global_stats = torch.zeros_like(stats)
         self._steps = 0
         self._side = torch.cuda.Stream(device=stats.device) if stats.is_cuda else None
@@ -38,9 +40,13 @@ class StatsReducer:
         if not (dist.is_available() and dist.is_initialized()):
             self.global_stats.copy_(self.stats)
             return
-        if self._side is None:
+        if self._side is None:                                    # CPU tensors (gloo): asynchronous work handle
             self.global_stats.copy_(self.stats)
             self._work = dist.all_reduce(self.global_stats, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            return
+        if self.inline:                                           # on the caller's stream, ordered with the env launches
+            self.global_stats.copy_(self.stats, non_blocking=True)
+            dist.all_reduce(self.global_stats, op=dist.ReduceOp.SUM, group=self.group)
             return
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.stats.device))
@@ -53,6 +59,6 @@ class StatsReducer:
         if self._work is not None:
             self._work.wait()
             self._work = None
-        if self._side is not None:
+        if self._side is not None and not self.inline:
             torch.cuda.current_stream(self.stats.device).wait_stream(self._side)
         return self.global_stats

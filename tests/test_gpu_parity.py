@@ -347,3 +347,39 @@ def test_host_env_matches_oracle(cw):
         assert np.array_equal(obs["observation"], o_obs), k
     assert np.array_equal(env.stats(), ob.stats)
     env.close()
+
+
+def test_no_out_of_bounds_writes_guard_bands(cw):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with canaries: every buffer the
+    kernels write is carved out of a larger allocation whose guard bands must stay untouched (odd sizes, auto-reset,
+    goal + init frames, multi-chunk frames at 64x64, tail groups)."""
+    GUARD = 4096
+    for size, N in ((21, 1031), (5, 77), (64, 37), (32, 300)):
+        env = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=9, seed=size)
+        pads = {}
+        for name in ("grid", "init_grid", "agent", "goal", "t", "episode", "reward", "_done_u8", "obs", "desired_goal", "init_obs"):
+            old = getattr(env, name)
+            nbytes = old.numel() * old.element_size()
+            raw = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
+            view = raw[GUARD:GUARD + nbytes].view(old.dtype).view(old.shape)
+            view.zero_()
+            setattr(env, name, view)
+            pads[name] = raw
+        env.done = env._done_u8.view(torch.bool)
+        env._obs_ring = [env.obs]
+        env._refresh_state_struct()
+        env.reset()
+        acts = torch.randint(0, 6, (40, N), device="cuda", dtype=torch.uint8)
+        for k in range(40):
+            env.step(acts[k])
+        env.render()
+        torch.cuda.synchronize()
+        for name, raw in pads.items():
+            assert bool((raw[:GUARD] == 0xA5).all()) and bool((raw[-GUARD:] == 0xA5).all()), f"{name} guard band hit at {size}x{size}"
+        ob = oracle_for(env, size)                     # and the run itself is still correct
+        ob.reset()
+        o_obs = ob.render()
+        for k in range(40):
+            ob.step_full(acts[k].cpu().numpy(), auto_reset=True, obs=o_obs)
+        assert_env_equals_oracle(env, ob, f"guarded {size}")
+        assert np.array_equal(env.obs.cpu().numpy(), o_obs)
