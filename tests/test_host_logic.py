@@ -100,3 +100,22 @@ def test_gif_recorder_writes_episode_gifs(tmp_path):
     with Image.open(rec.saved[0]) as im:
         assert im.n_frames == 4 and im.size == (40, 40)
     assert cw.register_envs() == []                       # neither gym nor gymnasium is installed here
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU only): exactly one JSON line on stdout with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "3", "--warmup", "3"], cwd=root,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
