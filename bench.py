@@ -216,7 +216,7 @@ def run_ours(args):
             ring *= 2
     env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=dev, auto_reset=True, obs_mode=wl["obs"],
                                      env_id_base=rank * N, obs_buffers=ring, goal_images=not args.no_goal_images,
-                                     max_steps=args.max_steps)
+                                     max_steps=args.max_steps, collect_stats=not args.no_stats)
     env.reset()
     if wl["dense"]:
         dense_worlds(env, torch, 99 + rank)
@@ -403,6 +403,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="shorter CPU baseline / e2e legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stats", action="store_true", help="experiment: do not accumulate episode statistics")
     ap.add_argument("--no-goal-images", action="store_true", help="experiment: skip imagine_obs / goal + init frames")
     ap.add_argument("--max-steps", type=int, default=300, help="experiment: episode length (reference default 300)")
     args = ap.parse_args()

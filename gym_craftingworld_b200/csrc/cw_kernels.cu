@@ -43,8 +43,10 @@ struct EnvArgs {
 __device__ unsigned long long* g_dbg = nullptr;   // [CTA][16] globaltimer stamps (experiments only)
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define CW_STAMP(slot) do { if (g_dbg && (threadIdx.x == 0 || (slot) >= 8) ) g_dbg[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+#define CW_WSTAMP(slot) do { if (g_dbg && (threadIdx.x & 31) == 0) g_dbg[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16 + (slot)] = gtimer(); } while (0)
 #else
 #define CW_STAMP(slot) do { } while (0)
+#define CW_WSTAMP(slot) do { } while (0)
 #endif
 
 enum : int { FL_RENDER = 1, FL_FRESH = 2, FL_GOAL = 4, FL_PENDING = 8 /* reset warp has work on this world */ };
@@ -65,7 +67,7 @@ enum : int { BAR_COMPOSE = 1, BAR_RESET_DONE = 2 };
 __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_lut[9];
-    __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32];
+    __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32], s_ep[32];
     __shared__ uint32_t s_flag[32];
     __shared__ uint32_t s_obj[8];
 
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     CW_STAMP(1);
 
     // tile + scalar prefetch of group `g` (tiles -> stage `sgi`; scalars -> registers of warp 0)
-    uint32_t p_agent = 0, p_goal = 0;
+    uint32_t p_agent = 0, p_goal = 0, p_ep = 0;
     int p_t = 0, p_a = 6, p_forced = 0;
     auto prefetch = [&](int64_t g, int sgi) {
         if (g < ngroups) {
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                 if (mode & (M_STEP | M_IMAGINE_ONLY)) p_goal = st.goal[e];
                 if (mode & M_STEP) { p_t = st.t[e]; p_a = args.actions[e]; }
                 if (mode & M_FORCE_RESET) p_forced = (!args.mask || args.mask[e]) ? 1 : 0;
+                if (mode & (M_AUTO_RESET | M_FORCE_RESET | M_IMAGINE_ONLY)) p_ep = st.episode[e];
             }
         }
         cp_async_commit();
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     prefetch(blockIdx.x, 0);
     for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
         // ---- A: this group's scalars move to `c_*`; the next group's tiles + scalars start loading ------------
-        const uint32_t c_agent = p_agent, c_goal = p_goal;
+        const uint32_t c_agent = p_agent, c_goal = p_goal, c_ep = p_ep;
         const int c_t = p_t, c_a = p_a, c_forced = p_forced;
         prefetch(gi + gridDim.x, stage ^ 1);
         cp_async_wait<1>();                                       // everything but the newest group has landed
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     }
                 }
             }
-            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; }
+            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; s_ep[lane] = c_ep; }
         }
         __syncthreads();
         CW_STAMP(3);
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                 uint32_t ag = s_agent[i], gl = s_goal[i];
                 if (!(mode & M_IMAGINE_ONLY)) {                   // reset(): ray.py:156-218
                     Sparse8 objs;
-                    reset_warp(cfg, st, er, tile, rng, ag, gl, &objs, s_obj);
+                    reset_warp(cfg, st, er, tile, rng, ag, gl, s_ep[i], &objs, s_obj);
                     if (lane == 0) { st.agent[er] = ag; st.goal[er] = gl; st.t[er] = 0; s_agent[i] = ag; }
                     flag |= FL_FRESH;
                     if (lane == 0 && st.init_agent) st.init_agent[er] = ag;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                         if (args.goal_obs) flag |= FL_GOAL;
                     }
                 } else {                                          // cw_imagine: arbitrary (dense) injected state
-                    rng.init(st.seed, st.env_id_base + (uint64_t)er, st.episode[er]);
+                    rng.init(st.seed, st.env_id_base + (uint64_t)er, s_ep[i]);
                     uint8_t* im = simag + i * cs;
                     for (int ch = lane; ch < nchunk16; ch += 32)
                         reinterpret_cast<uint4*>(im)[ch] = reinterpret_cast<const uint4*>(tile)[ch];
@@ -260,16 +263,18 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
 __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
                                                       int32_t* __restrict__ reward, uint8_t* __restrict__ done,
                                                       unsigned long long* stats, int K, int flags) {
+    CW_WSTAMP(0);
     pdl_launch_dependents();
     pdl_wait();
+    CW_WSTAMP(1);
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = n < st.n;
     const int64_t nn = valid ? n : 0;
     uint8_t* g = st.grid + nn * cfg.cell_stride;
     const uint8_t* ig = st.init_grid + nn * cfg.cell_stride;
-    uint32_t agent = 0, goal = 0;
+    uint32_t agent = 0, goal = 0, ep = 0;
     int t = 0;
-    if (valid) { agent = st.agent[n]; goal = st.goal[n]; t = st.t[n]; }
+    if (valid) { agent = st.agent[n]; goal = st.goal[n]; t = st.t[n]; ep = (flags & CW_F_AUTO_RESET) ? st.episode[n] : 0u; }
     for (int k = 0; k < K; k++) {
         bool dn = false;
         if (valid) {
@@ -282,18 +287,25 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
         }
         if (flags & CW_F_AUTO_RESET) {                            // finished worlds are re-seeded by the whole warp
             uint32_t m = __ballot_sync(0xffffffffu, valid && dn);
+            CW_WSTAMP(2);
+#ifdef CW_TIMING
+            if (g_dbg && (threadIdx.x & 31) == 0) g_dbg[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16 + 9] = __popc(m);
+#endif
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
                 const int64_t env = __shfl_sync(0xffffffffu, n, src);
+                const uint32_t env_ep = __shfl_sync(0xffffffffu, ep, src);
                 WarpPhilox rng;
                 uint32_t ag, gl;
-                reset_warp(cfg, st, env, nullptr, rng, ag, gl);
-                if (lane_id() == src) { agent = ag; goal = gl; t = 0; }
+                reset_warp(cfg, st, env, nullptr, rng, ag, gl, env_ep);
+                if (lane_id() == src) { agent = ag; goal = gl; t = 0; ep = env_ep + 1; }
             }
         }
     }
+    CW_WSTAMP(3);
     if (valid) { st.agent[n] = agent; st.goal[n] = goal; st.t[n] = t; }
+    CW_WSTAMP(4);
 }
 
 // observation_vector (ray.py:94-98, 605-613): one 32-bit word (4 of the 12 channel bytes of a cell) per thread

@@ -135,7 +135,7 @@ class BatchedCraftingWorldEnv:
     def __init__(self, num_envs, size=(STATE_W, STATE_H), fixed_init_state=0, max_steps=MAX_STEPS, store_gif=False,
                  render_save_rate=1, task_list=TASK_LIST, selected_tasks=TASK_LIST, number_of_tasks=None, stacking=True,
                  reward_style=None, *, device=None, seed=None, auto_reset=True, obs_mode="pixels", env_id_base=0,
-                 goal_images=True, obs_buffers=1, validate_actions=False):
+                 goal_images=True, obs_buffers=1, validate_actions=False, collect_stats=True):
         if store_gif:
             raise NotImplementedError("GIF recording (ray.py:565-597, 769-782) is a host-side debugging side channel; "
                                       "out of scope (DESIGN.md)")
@@ -161,6 +161,7 @@ class BatchedCraftingWorldEnv:
         self.auto_reset, self.obs_mode = bool(auto_reset), obs_mode
         self.goal_images = bool(goal_images) and obs_mode == "pixels"
         self.validate_actions = bool(validate_actions)
+        self.collect_stats = bool(collect_stats)
         self.env_id_base = int(env_id_base)
         self.compute_reward = self.compute_reward_equal if reward_style is None else self.compute_reward_subset
 
@@ -327,6 +328,9 @@ class BatchedCraftingWorldEnv:
     def _ptr(self, t):
         return None if t is None else t.data_ptr()
 
+    def _stats_ptr(self):
+        return self.stats.data_ptr() if self.collect_stats else None
+
     # ---- reset / step ------------------------------------------------------------------------------------
     def reset(self, mask=None):
         """``reset`` (``ray.py:156-218``) for all worlds, or for ``mask`` (bool/uint8 ``[N]``) only."""
@@ -368,13 +372,13 @@ class BatchedCraftingWorldEnv:
                     self.obs = self._obs_ring[self._ring_pos]
                 rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
                                               self._done_u8.data_ptr(), self.obs.data_ptr(), self._ptr(self.desired_goal),
-                                              self._ptr(self.init_obs), self.stats.data_ptr(), flags, self._stream())
+                                              self._ptr(self.init_obs), self._stats_ptr(), flags, self._stream())
             elif self.obs_mode == "onehot":       # no pixels, but resets must produce the imagined goal state
                 rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
-                                              self._done_u8.data_ptr(), None, None, None, self.stats.data_ptr(), flags, self._stream())
+                                              self._done_u8.data_ptr(), None, None, None, self._stats_ptr(), flags, self._stream())
             else:
                 rc = self._lib.cw_step(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
-                                       self._done_u8.data_ptr(), self.stats.data_ptr(), flags, self._stream())
+                                       self._done_u8.data_ptr(), self._stats_ptr(), flags, self._stream())
         _lib.check(rc, "cw_step")
         self._obs_version += 1
         return self._observation(), self.reward, self.done, self._info
@@ -394,7 +398,7 @@ class BatchedCraftingWorldEnv:
         flags = _lib.F_AUTO_RESET if self.auto_reset else 0
         with torch.cuda.device(self.device):
             _lib.check(self._lib.cw_rollout(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self._ptr(rew), self._ptr(dn),
-                                            self.stats.data_ptr(), K, flags, self._stream()), "cw_rollout")
+                                            self._stats_ptr(), K, flags, self._stream()), "cw_rollout")
         return (rew, dn.view(torch.bool)) if return_trace else None
 
     def render(self, state=None, mode="Non", tile_size=4):
