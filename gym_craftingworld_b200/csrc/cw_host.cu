@@ -6,11 +6,101 @@
 // slice j overlaps the kernel of slice j+1; PCIe, not the kernel, bounds this path when frames are returned.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "cw_b200.h"
+
+// ---- a small persistent worker pool for the host-side frame patching of the delta transport -----------------
+namespace {
+class WorkerPool {
+public:
+    explicit WorkerPool(int nthreads) : n_(nthreads < 1 ? 1 : nthreads) {
+        for (int i = 1; i < n_; i++) th_.emplace_back([this, i] { loop(i); });
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_.fetch_add(1); }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // run job(tid, nthreads) on every thread (the caller is tid 0); returns when all are done
+    void run(const std::function<void(int, int)>& job) {
+        job_ = &job;
+        remaining_.store(n_ - 1, std::memory_order_release);
+        { std::lock_guard<std::mutex> lk(m_); gen_.fetch_add(1, std::memory_order_release); }
+        cv_.notify_all();
+        job(0, n_);
+        while (remaining_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    }
+private:
+    void loop(int tid) {
+        uint64_t seen = 0;
+        for (;;) {
+            // stay hot while the caller is stepping back to back (a step is tens of microseconds); block after ~0.5 ms idle
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int spin = 0; gen_.load(std::memory_order_acquire) == seen; spin++) {
+                if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(500)) break;
+            }
+            if (gen_.load(std::memory_order_acquire) == seen) {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+            }
+            seen = gen_.load(std::memory_order_acquire);
+            if (stop_) return;
+            (*job_)(tid, n_);
+            remaining_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<int> remaining_{0};
+    const std::function<void(int, int)>* job_ = nullptr;
+    bool stop_ = false;
+};
+
+// COLORS_N (ray.py:28-30)
+const uint8_t kLut[9][3] = {{0, 0, 0},   {110, 69, 39},  {255, 105, 180}, {100, 100, 200}, {100, 100, 100},
+                            {0, 128, 0}, {205, 133, 63}, {197, 91, 97},   {240, 230, 140}};
+
+// one cell of a host frame: 4x4 pixels of the object's colour, agent overlay on top (ray.py:550-557)
+inline void patch_cell(uint8_t* frame, int W, int cell, int code, bool agent_here, int hold) {
+    const int r = cell / W, c = cell - r * W;
+    const size_t rowb = (size_t)12 * W;
+    uint8_t px[12];
+    for (int k = 0; k < 4; k++) memcpy(px + 3 * k, kLut[code], 3);
+    uint8_t* p = frame + (size_t)(4 * r) * rowb + 12 * c;
+    for (int y = 0; y < 4; y++) memcpy(p + y * rowb, px, 12);
+    if (agent_here) {
+        memset(p + rowb + 3, 255, 6);                                     // ray.py:555
+        if (hold) { memcpy(p + 2 * rowb + 3, kLut[hold], 3); memcpy(p + 2 * rowb + 6, kLut[hold], 3); }   // ray.py:556-557
+        else memset(p + 2 * rowb + 3, 255, 6);
+    }
+}
+// a whole host frame from a grid tile (ray.py:442-486): used for re-seeded worlds only
+inline void render_frame(uint8_t* frame, int H, int W, const uint8_t* g, uint32_t agent) {
+    const size_t rowb = (size_t)12 * W;
+    for (int br = 0; br < H; br++) {
+        uint8_t* row = frame + (size_t)(4 * br) * rowb;
+        for (int bc = 0; bc < W; bc++)
+            for (int k = 0; k < 4; k++) memcpy(row + 12 * bc + 3 * k, kLut[g[br * W + bc]], 3);
+        for (int k = 1; k < 4; k++) memcpy(row + k * rowb, row, rowb);
+    }
+    const int ar = agent & 0xFF, ac = (agent >> 8) & 0xFF, h = (agent >> 16) & 0xFF;
+    patch_cell(frame, W, ar * W + ac, g[ar * W + ac], true, h);
+}
+}  // namespace
 
 struct CwHostEnv {
     uint32_t magic;
@@ -28,6 +118,14 @@ struct CwHostEnv {
     size_t h_frames_bytes;
     cudaStream_t streams[2];
     int64_t slice;                    // worlds per slice
+    // delta transport (CW_F_DELTA_TRANSPORT)
+    uint4* h_delta;                   // pinned + mapped: per-world delta records written by the kernel
+    uint32_t* h_fresh;                // pinned + mapped: sparse records of re-seeded worlds
+    uint8_t* m_grid;                  // host mirror of the grids (the state the caller's frames show)
+    uint32_t* m_agent;                // host mirror of the agent words
+    uint8_t* mirror_obs;              // caller buffers the mirror currently describes
+    uint8_t* mirror_goal;
+    WorkerPool* pool;
 };
 
 #define CW_HOST_MAGIC 0x43574845u
@@ -62,7 +160,7 @@ extern "C" {
 int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, uint64_t env_id_base, int flags, CwHostEnv** out) {
     if (!cfg || !out) return CW_E_NULLPTR;
     if (n < 1) return CW_E_BADCONFIG;
-    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
+    if (flags & ~(CW_F_AUTO_RESET | CW_F_DELTA_TRANSPORT)) return CW_E_BADFLAGS;
     CK(cudaSetDevice(device));
     CwHostEnv* e = new (std::nothrow) CwHostEnv();
     if (!e) return (int)cudaErrorMemoryAllocation;
@@ -84,6 +182,20 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
     TRY(cudaMallocHost(&e->h_actions, n)); TRY(cudaMallocHost(&e->h_reward, n * 5));
     if (!rc) e->h_done = reinterpret_cast<uint8_t*>(e->h_reward) + n * 4;
     TRY(cudaMallocHost(&e->h_stats, CW_STATS_LEN * 8));
+    if (flags & CW_F_DELTA_TRANSPORT) {
+        TRY(cudaMallocHost(&e->h_delta, n * sizeof(uint4)));
+        TRY(cudaMallocHost(&e->h_fresh, n * CW_FRESH_WORDS * sizeof(uint32_t)));
+        if (!rc) {
+            e->m_grid = (uint8_t*)malloc(gb);
+            e->m_agent = (uint32_t*)malloc(n * 4);
+            if (!e->m_grid || !e->m_agent) rc = (int)cudaErrorMemoryAllocation;
+            unsigned hw = std::thread::hardware_concurrency();
+            int nt = (int)(hw ? hw : 4);
+            if (nt > 16) nt = 16;
+            if (nt > (int)(n / 128 + 1)) nt = (int)(n / 128 + 1);
+            e->pool = new (std::nothrow) WorkerPool(nt);
+        }
+    }
     TRY(cudaStreamCreateWithFlags(&e->streams[0], cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&e->streams[1], cudaStreamNonBlocking));
     if (!rc) {
@@ -123,6 +235,70 @@ int cw_host_reset(CwHostEnv* e, uint8_t* obs_host, uint8_t* goal_obs_host) {
         }
     }
     CK(cudaStreamSynchronize(s));
+    if (e->flags & CW_F_DELTA_TRANSPORT) {                       // (re)build the host mirror
+        CK(cudaMemcpy(e->m_grid, e->st.grid, (size_t)e->st.n * e->cfg.cell_stride, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(e->m_agent, e->st.agent, (size_t)e->st.n * 4, cudaMemcpyDeviceToHost));
+        e->mirror_obs = obs_host;
+        e->mirror_goal = goal_obs_host;
+    }
+    return 0;
+}
+
+// delta transport: one launch writing 16-byte records into mapped pinned memory, then the pool patches the frames
+static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward_host, uint8_t* done_host, uint8_t* obs_host) {
+    cudaStream_t s = e->streams[0];
+    const int64_t n = e->st.n;
+    const int H = e->cfg.H, W = e->cfg.W, cs = e->cfg.cell_stride;
+    if (obs_host != e->mirror_obs) {                              // unknown buffer: one full refresh, then deltas
+        int rc = cw_render(&e->cfg, e->st.grid, e->st.agent, e->d_obs, n, s);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(obs_host, e->d_obs, (size_t)n * e->frame_bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(e->m_grid, e->st.grid, (size_t)n * cs, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(e->m_agent, e->st.agent, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        e->mirror_obs = obs_host;
+    }
+    int rc = cw_step_delta(&e->cfg, &e->st, act_src, e->h_delta, e->h_fresh, e->d_stats, e->flags & CW_F_AUTO_RESET, s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    const size_t fb = e->frame_bytes;
+    uint8_t* goal = e->mirror_goal;
+    const std::function<void(int, int)> job = [=](int tid, int nt) {
+        const int64_t lo = n * tid / nt, hi = n * (tid + 1) / nt;
+        uint8_t tmp[CW_MAX_SIDE * CW_MAX_SIDE];
+        for (int64_t w = lo; w < hi; w++) {
+            const uint4 r = e->h_delta[w];
+            const uint32_t flags = r.z >> 24;
+            reward_host[w] = (int32_t)r.w;
+            done_host[w] = (uint8_t)(flags & 1u);
+            uint8_t* g = e->m_grid + w * cs;
+            uint8_t* frame = obs_host + w * fb;
+            if (flags & 2u) {                                     // re-seeded: rebuild tile + frame (+ goal frame)
+                const uint32_t* fr = e->h_fresh + w * CW_FRESH_WORDS;
+                memset(g, 0, cs);
+                for (int k = 0; k < 8; k++) if (fr[k] >> 16) g[fr[k] & 0xFFFFu] = (uint8_t)(fr[k] >> 16);
+                e->m_agent[w] = r.x;
+                render_frame(frame, H, W, g, r.x);
+                if (goal) {
+                    memset(tmp, 0, (size_t)H * W);
+                    for (int k = 8; k < 16; k++) if (fr[k] >> 16) tmp[fr[k] & 0xFFFFu] = (uint8_t)(fr[k] >> 16);
+                    render_frame(goal + w * fb, H, W, tmp, fr[16]);
+                }
+            } else {                                              // patch the <= 3 cells that changed (render_edit)
+                const uint32_t old = e->m_agent[w];
+                const int wcell = (int)(r.z & 0xFFFFu);
+                if (wcell != 0xFFFF) g[wcell] = (uint8_t)((r.z >> 16) & 0xFFu);
+                if (wcell == 0xFFFF && old == r.x) continue;      // nothing visible changed
+                e->m_agent[w] = r.x;
+                const int oc = (int)(old & 0xFF) * W + (int)((old >> 8) & 0xFF);
+                const int nc = (int)(r.x & 0xFF) * W + (int)((r.x >> 8) & 0xFF), hold = (int)((r.x >> 16) & 0xFF);
+                if (oc != nc) patch_cell(frame, W, oc, g[oc], false, 0);
+                if (wcell != 0xFFFF && wcell != nc && wcell != oc) patch_cell(frame, W, wcell, g[wcell], false, 0);
+                patch_cell(frame, W, nc, g[nc], true, hold);
+            }
+        }
+    };
+    e->pool->run(job);
     return 0;
 }
 
@@ -131,18 +307,19 @@ int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host
     if (!actions_host || !reward_host || !done_host) return CW_E_NULLPTR;
     CK(cudaSetDevice(e->device));
     const int64_t n = e->st.n;
+    const uint8_t* act_src = actions_host;
+    if (!is_pinned(actions_host)) { memcpy(e->h_actions, actions_host, n); act_src = e->h_actions; }
+    if (obs_host && (e->flags & CW_F_DELTA_TRANSPORT)) return host_step_delta(e, act_src, reward_host, done_host, obs_host);
     const bool direct = obs_host && is_pinned(obs_host);
     uint8_t* frames_dst = obs_host;
     if (obs_host && !direct) { int rc = ensure_frame_staging(e); if (rc) return rc; frames_dst = e->h_frames; }
-    const uint8_t* act_src = actions_host;
-    if (!is_pinned(actions_host)) { memcpy(e->h_actions, actions_host, n); act_src = e->h_actions; }
     if (!obs_host) {
         // Frames stay in HBM for a device-side consumer.  Zero-copy: the kernel reads the actions from, and writes
         // reward/done to, mapped pinned host memory (UVA), so a step is ONE launch + ONE stream sync -- no memcpy
         // launches on the critical path.
         cudaStream_t s = e->streams[0];
         int rc = cw_step_render(&e->cfg, &e->st, act_src /* pinned: the caller's own buffer or our staging copy */, e->h_reward, e->h_done, e->d_obs, e->d_goal_obs, nullptr,
-                                e->d_stats, e->flags, s);
+                                e->d_stats, e->flags & CW_F_AUTO_RESET, s);
         if (rc) return rc;
         CK(cudaStreamSynchronize(s));
     } else {
@@ -154,7 +331,7 @@ int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host
             CwState sl = slice_state(e, off, cnt);
             int rc = cw_step_render(&e->cfg, &sl, e->d_actions + off, e->d_reward + off, e->d_done + off,
                                     e->d_obs + (size_t)off * e->frame_bytes, e->d_goal_obs + (size_t)off * e->frame_bytes, nullptr,
-                                    e->d_stats, e->flags, s);
+                                    e->d_stats, e->flags & CW_F_AUTO_RESET, s);
             if (rc) return rc;
             CK(cudaMemcpyAsync(e->h_reward + off, e->d_reward + off, cnt * 4, cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(e->h_done + off, e->d_done + off, cnt, cudaMemcpyDeviceToHost, s));
@@ -195,6 +372,10 @@ int cw_host_destroy(CwHostEnv* e) {
     cudaFree(e->d_goal_obs); cudaFree(e->d_stats);
     cudaFreeHost(e->h_actions); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_stats);
     if (e->h_frames) cudaFreeHost(e->h_frames);
+    if (e->h_delta) cudaFreeHost(e->h_delta);
+    if (e->h_fresh) cudaFreeHost(e->h_fresh);
+    free(e->m_grid); free(e->m_agent);
+    delete e->pool;
     if (e->streams[0]) cudaStreamDestroy(e->streams[0]);
     if (e->streams[1]) cudaStreamDestroy(e->streams[1]);
     e->magic = 0;

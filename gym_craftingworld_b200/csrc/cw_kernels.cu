@@ -30,6 +30,8 @@ struct EnvArgs {
     uint8_t* goal_obs;
     uint8_t* init_obs;       // INIT_OBS copy of the first frame of a new episode (ray.py:193), nullable
     unsigned long long* stats;
+    uint4* delta;            // delta transport: per-world record {agent, goal, wcell | wval<<16 | flags<<24, reward} (nullable)
+    uint32_t* fresh;         // delta transport: [N][CW_FRESH_WORDS] sparse record of a re-seeded world + its imagined goal
     const uint8_t* rgrid;    // render-only entry: grid / agent given directly (state may be partial)
     const uint32_t* ragent;
     int mode;
@@ -67,7 +69,7 @@ enum : int { BAR_COMPOSE = 1, BAR_RESET_DONE = 2 };
 __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_lut[9];
-    __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32], s_ep[32];
+    __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32], s_ep[32], s_rew[32];
     __shared__ uint32_t s_flag[32];
     __shared__ uint32_t s_obj[8];
 
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
             const int lane = tid;
             const int64_t e = e0 + lane;
             const bool valid = lane < G && e < st.n;
-            uint32_t agent = c_agent, goal = c_goal, flag = 0;
+            uint32_t agent = c_agent, goal = c_goal, flag = 0, rew_stash = 0;
             if (valid) {
                 const bool skip = (mode & M_FORCE_RESET) && !c_forced;   // masked reset: untouched worlds are skipped
                 if (!skip && (mode & M_RENDER)) flag |= FL_RENDER;
@@ -163,17 +165,21 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     bool dn;
                     const int rew = step_core(cfg, gt + lane * cs, st.init_grid + e * cs, agent, goal, t, c_a, dn, wcell, wval);
                     if (wcell >= 0) st.grid[e * cs + wcell] = (uint8_t)wval;
-                    args.reward[e] = rew;
-                    args.done[e] = dn ? 1 : 0;
+                    if (args.reward) args.reward[e] = rew;
+                    if (args.done) args.done[e] = dn ? 1 : 0;
                     if (dn && (mode & M_AUTO_RESET)) {
                         flag |= FL_PENDING;
                         if (args.stats) stats_add(cfg, args.stats, goal, t, rew);
                     } else {
                         st.agent[e] = agent; st.goal[e] = goal; st.t[e] = t;
+                        if (args.delta)                           // one 16-byte store (possibly into mapped host memory)
+                            args.delta[e] = make_uint4(agent, goal, (uint32_t)(wcell & 0xFFFF) | ((uint32_t)wval << 16) | ((dn ? 1u : 0u) << 24),
+                                                       (uint32_t)rew);
                     }
+                    rew_stash = (uint32_t)rew;
                 }
             }
-            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; s_ep[lane] = c_ep; }
+            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; s_ep[lane] = c_ep; s_rew[lane] = rew_stash; }
         }
         __syncthreads();
         CW_STAMP(3);
@@ -193,9 +199,26 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     if (lane == 0) { st.agent[er] = ag; st.goal[er] = gl; st.t[er] = 0; s_agent[i] = ag; }
                     flag |= FL_FRESH;
                     if (lane == 0 && st.init_agent) st.init_agent[er] = ag;
-                    if (args.goal_obs || st.goal_grid) {          // desired_goal = imagine_obs(): ray.py:191, 220-299
+                    if (args.delta) {                             // delta transport: the new world as a sparse list
+                        uint32_t* fr = args.fresh + (size_t)er * CW_FRESH_WORDS;
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) word = lane == k ? (objs.cell[k] | (objs.code[k] << 16)) : word;
+                        if (lane < 8) fr[lane] = word;
+                        if (lane == 0)
+                            args.delta[er] = make_uint4(ag, gl, 0xFFFFu | (3u << 24) /* done | fresh */, s_rew[i]);
+                    }
+                    if (args.goal_obs || st.goal_grid || args.delta) {   // desired_goal = imagine_obs(): ray.py:191, 220-299
                         uint32_t gag = ag;
                         imagine_fresh(cfg, objs, gag, gl >> 16, rng);      // closed form on the 8-object list
+                        if (args.delta) {
+                            uint32_t* fr = args.fresh + (size_t)er * CW_FRESH_WORDS;
+                            uint32_t word = 0;
+#pragma unroll
+                            for (int k = 0; k < 8; k++) word = lane == k ? (objs.cell[k] | (objs.code[k] << 16)) : word;
+                            if (lane < 8) fr[8 + lane] = word;
+                            if (lane == 8) fr[16] = gag;
+                        }
                         tile_from_objects(objs, nchunk16, simag + i * cs);
                         if (st.goal_grid) {                       // compact goal state (one-hot observation family)
                             for (int ch = lane; ch < nchunk16; ch += 32)
@@ -584,6 +607,21 @@ int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* action
     a.actions = actions; a.reward = reward; a.done = done; a.obs = obs; a.goal_obs = goal_obs; a.init_obs = init_obs;
     a.stats = (unsigned long long*)stats;
     a.mode = M_STEP | (obs ? M_RENDER : 0) | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
+    return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
+}
+
+int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions, void* delta, uint32_t* fresh, int64_t* stats,
+                  int flags, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    rc = check_state(st); if (rc) return rc;
+    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
+    if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
+    if (st->n == 0) return 0;
+    if (!actions || !delta || !fresh) return CW_E_NULLPTR;
+    EnvArgs a = {};
+    a.actions = actions; a.delta = (uint4*)delta; a.fresh = fresh; a.stats = (unsigned long long*)stats;
+    a.reward = nullptr; a.done = nullptr;
+    a.mode = M_STEP | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
     return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
 }
 

@@ -26,7 +26,12 @@ def pinned_empty(shape, dtype):
 class HostCraftingWorldEnv:
     def __init__(self, num_envs, size=(STATE_W, STATE_H), max_steps=MAX_STEPS, task_list=TASK_LIST,
                  selected_tasks=TASK_LIST, number_of_tasks=None, stacking=True, reward_style=None, *, device=0, seed=0,
-                 auto_reset=True, env_id_base=0, return_frames=True):
+                 auto_reset=True, env_id_base=0, return_frames=True, transport="frames"):
+        """``transport``: how frames reach host memory when ``return_frames`` -- ``"frames"`` copies every frame over PCIe;
+        ``"delta"`` ships a 16-byte delta per world and patches the pinned frame mirror on the host (bit-identical frames)."""
+        if transport not in ("frames", "delta"):
+            raise ValueError("transport must be 'frames' or 'delta'")
+        self.transport = transport
         self.num_envs = int(num_envs)
         self.cfg = make_config(size, max_steps, task_list, selected_tasks, number_of_tasks, stacking, reward_style)
         self._lib = _lib.load()
@@ -35,7 +40,7 @@ class HostCraftingWorldEnv:
         self.device = int(device)
         self.return_frames = bool(return_frames)
         self._h = C.c_void_p()
-        flags = _lib.F_AUTO_RESET if auto_reset else 0
+        flags = (_lib.F_AUTO_RESET if auto_reset else 0) | (_lib.F_DELTA_TRANSPORT if (transport == "delta" and return_frames) else 0)
         _lib.check(self._lib.cw_host_create(C.byref(self.cfg), self.num_envs, self.device, C.c_uint64(int(seed)),
                                             C.c_uint64(int(env_id_base)), flags, C.byref(self._h)), "cw_host_create")
         N, H, W = self.num_envs, self.cfg.H, self.cfg.W
@@ -52,6 +57,8 @@ class HostCraftingWorldEnv:
 
     @property
     def d2h_bytes_per_step(self) -> int:
+        if self.return_frames and self.transport == "delta":
+            return self.num_envs * 16           # delta records (+ 72 B per re-seeded world, ~1/300 of the worlds per step)
         return self.num_envs * 5 + (int(np.prod(self.frame_shape)) if self.return_frames else 0)
 
     def _p(self, a):

@@ -41,6 +41,7 @@ extern "C" {
 #define CW_ABI_VERSION 1
 #define CW_STATS_LEN 24
 #define CW_MAX_SIDE 64 /* H, W <= 64 (cell_stride <= 4096) */
+#define CW_FRESH_WORDS 18 /* delta transport: uint32 words of a re-seeded world's sparse record (see cw_step_delta) */
 
 /* argument errors */
 #define CW_E_BADCONFIG (-1)
@@ -51,6 +52,8 @@ extern "C" {
 /* flags */
 #define CW_F_AUTO_RESET 1 /* on done: add the episode to stats, Philox-reset the world in the same launch; the
                              returned reward/done are the finished episode's, state/obs the new episode's */
+#define CW_F_DELTA_TRANSPORT 2 /* cw_host_create only: keep the caller's frame buffer current by delta records + host-side
+                                  patching of the changed cells instead of copying every frame over PCIe */
 
 /* Constructor arguments of the reference that reach the hot path (ray.py:59-83). */
 typedef struct CwConfig {
@@ -116,6 +119,17 @@ int cw_render(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, u
 int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
                    uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, void* stream);
 
+/* step + auto-reset WITHOUT device frames, for a host-side frame mirror ("delta transport"): instead of 48*H*W bytes of
+ * pixels per world, each world gets one 16-byte record
+ *     delta[n] = { agent, goal, wcell | wval<<16 | flags<<24, reward }      flags: 1 done, 2 fresh (re-seeded)
+ * (wcell = 0xFFFF: no grid cell written this step), and a world re-seeded in this call additionally gets
+ *     fresh[n][0..7]  = cell | code<<16 of its 8 objects        fresh[n][8..15] = same for the imagined goal state
+ *     fresh[n][16]    = agent word of the imagined goal state
+ * `delta` / `fresh` may point into mapped pinned HOST memory (zero-copy): the consumer patches the <= 3 cells that changed
+ * in its own copy of the frame (what the reference's render_edit does, ray.py:522-557). */
+int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions, void* delta /* uint4[N] */,
+                  uint32_t* fresh /* [N][CW_FRESH_WORDS] */, int64_t* stats, int flags, void* stream);
+
 /* K consecutive steps in one launch (open-loop action tape actions[K][N]); reward/done [K][N] nullable.
  * Same per-step semantics as cw_step. */
 int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
@@ -147,6 +161,9 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
 int cw_host_reset(CwHostEnv* env, uint8_t* obs_host /*nullable*/, uint8_t* goal_obs_host /*nullable*/);
 int cw_host_step(CwHostEnv* env, const uint8_t* actions_host, int32_t* reward_host, uint8_t* done_host,
                  uint8_t* obs_host /*nullable: pixels stay on the device*/);
+/* With CW_F_DELTA_TRANSPORT, obs_host (and the goal buffer given to cw_host_reset) are persistent mirrors owned by the
+ * caller: pass the same pointers every call; the library patches them in place (a different pointer triggers one full
+ * refresh).  After every call they hold exactly the frames a full device render + copy would have produced. */
 int cw_host_stats(CwHostEnv* env, int64_t* stats_host /*[CW_STATS_LEN]*/);
 /* device pointers of the handle's state, for callers that DO have a device-side consumer (e.g. a policy) */
 int cw_host_device_state(CwHostEnv* env, CwState* out_state, uint8_t** out_obs);

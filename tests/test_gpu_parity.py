@@ -383,3 +383,28 @@ def test_no_out_of_bounds_writes_guard_bands(cw):
             ob.step_full(acts[k].cpu().numpy(), auto_reset=True, obs=o_obs)
         assert_env_equals_oracle(env, ob, f"guarded {size}")
         assert np.array_equal(env.obs.cpu().numpy(), o_obs)
+
+
+@pytest.mark.parametrize("size,N,max_steps", [(21, 3000, 15), (5, 700, 6), (32, 260, 20)])
+def test_host_env_delta_transport_matches_oracle(cw, size, N, max_steps):
+    """Delta transport: the device ships 16-byte records, the host library patches the caller's pinned frame mirror.
+    After EVERY step the host frames must equal the oracle's full render (incl. re-seeded worlds and goal frames)."""
+    seed, K = 91, 60
+    env = cw.HostCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=seed, transport="delta")
+    ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed)
+    obs = env.reset()
+    o_goal = ob.reset(with_goal=True)
+    o_obs = ob.render()
+    assert np.array_equal(obs["observation"], o_obs) and np.array_equal(obs["desired_goal"], o_goal)
+    rng = np.random.RandomState(2)
+    new_goal = np.zeros_like(o_goal)
+    for k in range(K):
+        a = rng.randint(0, 6, N)
+        obs, reward, done, _ = env.step(a)
+        o_reward, o_done = ob.step_full(a.astype(np.uint8), auto_reset=True, obs=o_obs, goal_obs=new_goal)
+        o_goal[o_done == 1] = new_goal[o_done == 1]
+        assert np.array_equal(reward, o_reward) and np.array_equal(done, o_done.astype(bool)), k
+        assert np.array_equal(obs["observation"], o_obs), f"host frame mirror diverged at step {k}"
+        assert np.array_equal(obs["desired_goal"], o_goal), f"host goal mirror diverged at step {k}"
+    assert np.array_equal(env.stats(), ob.stats) and ob.stats[0] > 0
+    env.close()
