@@ -5,6 +5,7 @@
 // an obs buffer is passed) come back device->host.  Slices alternate between two streams so the D2H copy of
 // slice j overlaps the kernel of slice j+1; PCIe, not the kernel, bounds this path when frames are returned.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -131,6 +132,23 @@ struct CwHostEnv {
 #define CW_HOST_MAGIC 0x43574845u
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
+// worker threads of the delta transport: the cores this process may run on, shared fairly between the ranks of the node
+// (LOCAL_WORLD_SIZE is set by torchrun), at most 16, at least 1; CW_HOST_THREADS overrides.
+static int host_threads(int64_t n) {
+    if (const char* s = getenv("CW_HOST_THREADS")) { const int v = atoi(s); if (v > 0) return v > 64 ? 64 : v; }
+    int cores = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+    if (cores <= 0) cores = (int)std::thread::hardware_concurrency();
+    if (cores <= 0) cores = 4;
+    int ranks = 1;
+    if (const char* s = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(s); if (v > 0) ranks = v; }
+    int nt = cores / ranks;
+    if (nt > 16) nt = 16;
+    if (nt > (int)(n / 128 + 1)) nt = (int)(n / 128 + 1);
+    return nt < 1 ? 1 : nt;
+}
+
 static bool is_pinned(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -189,11 +207,7 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
             e->m_grid = (uint8_t*)malloc(gb);
             e->m_agent = (uint32_t*)malloc(n * 4);
             if (!e->m_grid || !e->m_agent) rc = (int)cudaErrorMemoryAllocation;
-            unsigned hw = std::thread::hardware_concurrency();
-            int nt = (int)(hw ? hw : 4);
-            if (nt > 16) nt = 16;
-            if (nt > (int)(n / 128 + 1)) nt = (int)(n / 128 + 1);
-            e->pool = new (std::nothrow) WorkerPool(nt);
+            e->pool = new (std::nothrow) WorkerPool(host_threads(n));
         }
     }
     TRY(cudaStreamCreateWithFlags(&e->streams[0], cudaStreamNonBlocking));
