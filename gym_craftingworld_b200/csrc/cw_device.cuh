@@ -335,66 +335,13 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
     __syncwarp();
 }
 
-// warp-cooperative scans over a shared-memory grid tile, in np.where (row-major) order.
-// A lane owns one 16-byte chunk (16 cells) per pass: byte-SIMD compare (__vcmpeq4) -> 16-bit match mask, so a
-// 21x21 tile (28 chunks) is one pass.  Cells >= n (row padding) and the `skip` cell never match.
-__device__ __forceinline__ uint32_t match_mask16(const uint8_t* g, int chunk, int n, int code, int skip) {
-    const uint4 v = reinterpret_cast<const uint4*>(g)[chunk];
-    const uint32_t pat = (uint32_t)code * 0x01010101u;
-    auto nib = [&](uint32_t w) {   // byte-equality -> 4 bits (multiply gathers bits 0,8,16,24 into 24..27)
-        return ((((__vcmpeq4(w, pat) >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
-    };
-    uint32_t m = nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
-    const int left = n - 16 * chunk;                     // valid cells in this chunk
-    if (left < 16) m &= left > 0 ? ((1u << left) - 1u) : 0u;
-    const int sk = skip - 16 * chunk;
-    if (sk >= 0 && sk < 16) m &= ~(1u << sk);
-    return m;
-}
+// warp-cooperative scans over a shared-memory grid tile, in np.where (row-major) order, 32 cells per pass.
+// (A 16-cells-per-lane byte-SIMD variant was measured slower on this latency-bound path)
 // position of the j-th (0-based) set bit of m; j < popc(m).  (__fns is software-emulated and slow.)
 __device__ __forceinline__ int nth_set_bit(uint32_t m, int j) {
     for (int i = 0; i < j; i++) m &= m - 1;
     return __ffs(m) - 1;
 }
-#ifndef CW_SCAN_SIMD
-#define CW_SCAN_SIMD 0   // measured on B200: the plain 32-cells-per-pass loop is faster on this serial path (A/B, same box)
-#endif
-#if CW_SCAN_SIMD
-__device__ __forceinline__ int warp_count(const uint8_t* g, int n, int code, int skip) {
-    const int nchunk = (n + 15) >> 4;
-    int cnt = 0;
-    for (int base = 0; base < nchunk; base += 32) {
-        const int ch = base + lane_id();
-        cnt += ch < nchunk ? __popc(match_mask16(g, ch, n, code, skip)) : 0;
-    }
-    return (int)__reduce_add_sync(0xffffffffu, (unsigned)cnt);
-}
-__device__ __forceinline__ int warp_nth(const uint8_t* g, int n, int code, int k, int skip) {
-    const int nchunk = (n + 15) >> 4;
-    const int lane = lane_id();
-    for (int base = 0; base < nchunk; base += 32) {
-        const int ch = base + lane;
-        const uint32_t m = ch < nchunk ? match_mask16(g, ch, n, code, skip) : 0u;
-        const int c = __popc(m);
-        int incl = c;                                     // inclusive prefix sum over lanes
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (k < total) {
-            const uint32_t hit = __ballot_sync(0xffffffffu, incl > k);
-            const int owner = __ffs(hit) - 1;
-            int pos = 0;
-            if (lane == owner) pos = nth_set_bit(m, k - (incl - c));
-            return __shfl_sync(0xffffffffu, 16 * ch + pos, owner);
-        }
-        k -= total;
-    }
-    return -1;
-}
-#else
 __device__ __forceinline__ int warp_count(const uint8_t* g, int n, int code, int skip) {
     int cnt = 0;
     for (int base = 0; base < n; base += 32) {
@@ -415,7 +362,6 @@ __device__ __forceinline__ int warp_nth(const uint8_t* g, int n, int code, int k
     }
     return -1;
 }
-#endif
 __device__ __forceinline__ void warp_set(uint8_t* g, int cell, int code) {
     __syncwarp();
     if (lane_id() == 0) g[cell] = (uint8_t)code;
@@ -603,9 +549,6 @@ __device__ __forceinline__ void tile_from_objects(const Sparse8& o, int nchunk, 
 // owner of the agent cell patches rows 1,2 itself (2x2 white block :483, bottom row = held colour :484-486),
 // so no second pass / barrier is needed.  Lanes hit consecutive cells => word stride 3 => conflict-free STS.
 // ------------------------------------------------------------------------------------------------------
-#ifndef CW_COMPOSE_BANDWISE
-#define CW_COMPOSE_BANDWISE 0
-#endif
 __device__ __forceinline__ void compose_cell(const uint8_t* __restrict__ src, int i, int b, int col, int roww, int acell,
                                              uint32_t hc, uint32_t* __restrict__ frame, const uint32_t* __restrict__ slut) {
     const uint32_t rgb = slut[src[i]];
@@ -630,36 +573,21 @@ __device__ __forceinline__ void compose_bands(const CwConfig& cfg, const uint8_t
     const int acell = ar * W + ac - band0 * W;
     const uint32_t hc = ah ? slut[ah] : 0x00FFFFFFu;
     const uint8_t* src = sg + band0 * W;
-#if CW_COMPOSE_BANDWISE
-    // one band (cell row) per warp pass: lanes = columns, so a warp-wide STS never straddles a band boundary
-    const int lane = ctid & 31, warp = ctid >> 5, nwarps = cthreads >> 5;
-    for (int b = warp; b < nbands; b += nwarps)
-        for (int col = lane; col < W; col += 32) compose_cell(src, b * W + col, b, col, roww, acell, hc, frame, slut);
-#else
     const int ncells = nbands * W;
     for (int i = ctid; i < ncells; i += cthreads) {
         const int b = (int)__umulhi((uint32_t)i, w_magic);   // i / W
         compose_cell(src, i, b, i - b * W, roww, acell, hc, frame, slut);
     }
-#endif
 }
 
 // ---- TMA bulk store (shared::cta -> global), sm_90+ : SASS UBLKCP ---------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-#ifndef CW_STORE_EVICT_FIRST
-#define CW_STORE_EVICT_FIRST 1   // measured (A/B, same box): +2.9% at 4096 worlds, +0.5% at 131072
-#endif
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-#if CW_STORE_EVICT_FIRST
-    uint64_t pol;   // streaming frames: ask L2 to evict them first
+    uint64_t pol;   // streaming frames: ask L2 to evict them first (measured A/B: +2.9% at 4096 worlds, +0.5% at 131072)
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(ssrc)),
                  "r"(bytes), "l"(pol) : "memory");
-#else
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
-                 : "memory");
-#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int kPending>

@@ -38,6 +38,7 @@ struct EnvArgs {
     int group;               // G: worlds per CTA iteration (<= 32); their steps run lane-parallel in warp 0
     int nbuf;                // F: frame-chunk ring slots (2..4)
     int bands_per_chunk;
+    int first_split;         // the first frame of a launch is stored in this many pieces (earlier first store)
     uint32_t w_magic;        // floor(2^32 / W) + 1
 };
 
@@ -119,10 +120,11 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     };
 
     int slot = 0;                                                 // ring slot of the next frame chunk
+    const int first_bands = max(1, (args.bands_per_chunk + args.first_split - 1) / args.first_split);
     // expand one world (tile `src`) into the ring and stream it to dst (and dst2 when non-null); compose warps only
-    auto emit_frame = [&](const uint8_t* src, uint32_t ag, uint8_t* dst, uint8_t* dst2) {
-        for (int band0 = 0; band0 < H; band0 += args.bands_per_chunk) {
-            const int nb = min(args.bands_per_chunk, H - band0);
+    auto emit_frame = [&](const uint8_t* src, uint32_t ag, uint8_t* dst, uint8_t* dst2, int bands_per_store) {
+        for (int band0 = 0; band0 < H; band0 += bands_per_store) {
+            const int nb = min(bands_per_store, H - band0);
             uint8_t* fb = ring + (size_t)slot * chunk_bytes;
             compose_bands(cfg, src, ag, band0, nb, reinterpret_cast<uint32_t*>(fb), s_lut, args.w_magic, tid, kComposeThreads);
             fence_proxy_async_smem();
@@ -255,11 +257,15 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
             bar_arrive(BAR_RESET_DONE, kEnvThreads);
         } else {
             // ---- C: expand + stream out: untouched worlds first, worlds from the reset warp after its arrival ------
+            // the very first frame of the launch goes out in quarter-frame stores: the launch is bound by the DRAM
+            // write-back window that opens with the first store, so open it as early as possible
+            bool first = gi == (int64_t)blockIdx.x;
             for (int i = 0; i < G; i++) {
                 const uint32_t flag = s_flag[i];
                 if (!(flag & FL_RENDER) || (flag & FL_PENDING)) continue;
                 const size_t off = (size_t)(e0 + i) * frame_bytes;
-                emit_frame(gt + i * cs, s_agent[i], args.obs + off, nullptr);
+                emit_frame(gt + i * cs, s_agent[i], args.obs + off, nullptr, first ? first_bands : args.bands_per_chunk);
+                first = false;
             }
             CW_STAMP(4);
             bar_sync(BAR_RESET_DONE, kEnvThreads);
@@ -268,9 +274,10 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                 const uint32_t flag = s_flag[i];
                 if (!(flag & FL_PENDING)) continue;
                 const size_t off = (size_t)(e0 + i) * frame_bytes;
-                if (flag & FL_GOAL) emit_frame(simag + i * cs, s_gagent[i], args.goal_obs + off, nullptr);
+                if (flag & FL_GOAL) emit_frame(simag + i * cs, s_gagent[i], args.goal_obs + off, nullptr, args.bands_per_chunk);
                 if (flag & FL_RENDER)
-                    emit_frame(gt + i * cs, s_agent[i], args.obs + off, ((flag & FL_FRESH) && args.init_obs) ? args.init_obs + off : nullptr);
+                    emit_frame(gt + i * cs, s_agent[i], args.obs + off, ((flag & FL_FRESH) && args.init_obs) ? args.init_obs + off : nullptr,
+                               args.bands_per_chunk);
             }
         }
         CW_STAMP(6);
@@ -480,6 +487,8 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     args.nbuf = F;
     args.bands_per_chunk = needs_frame ? pick_bands(cfg, env_tunable("CW_CHUNK_BYTES", 25 * 1024)) : 1;
     args.w_magic = (uint32_t)(0x100000000ull / (uint64_t)cfg->W) + 1u;
+    args.first_split = env_tunable("CW_FIRST_SPLIT", 4);
+    if (args.first_split < 1) args.first_split = 1;
     const size_t ring = needs_frame ? (size_t)F * 48 * cfg->W * args.bands_per_chunk : 0;
     const int cap = env_tunable("CW_CTAS_PER_SM", 0);
     // group size G: the per-SM critical path is (CTA waves) x G worlds; pick the G that minimises it

@@ -6,7 +6,7 @@ import gym_craftingworld_b200 as cw
 from gym_craftingworld_b200 import _lib
 lib = _lib.load()
 N = 4096
-env = cw.BatchedCraftingWorldEnv(N, seed=0, obs_buffers=4, max_steps=int(os.environ.get("MAXS", "300")))
+env = cw.BatchedCraftingWorldEnv(N, seed=0, obs_buffers=int(os.environ.get("RING", "4")), max_steps=int(os.environ.get("MAXS", "300")))
 env.reset()
 tape = torch.randint(0, 6, (128, N), device="cuda", dtype=torch.uint8)
 for k in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3000):
@@ -26,6 +26,7 @@ for rep in range(12):
     npend = d[:, 9].astype(int)
     hr = npend > 0
     def f(x): return "%.2f" % x
+    print("tiles landed (mean after wait release) %.2f | step done %.2f |" % ((r[:, 2] - r[:, 1]).mean(), (r[:, 3] - r[:, 2]).mean()), end=" ")
     print("launch: ctas", len(d), "work span (first past-wait -> last exit)", f(r[:, 7].max()), "us | exit mean", f(r[:, 7].mean()),
           "| no-reset CTAs: C1done", f(r[~hr, 4].mean()), "exit max", f(r[~hr, 7].max()),
           "| reset CTAs", int(hr.sum()), "pending worlds", int(npend.sum()))
