@@ -593,10 +593,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int kPending>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_dyn(int pending) {   // pending in 0..2
+__device__ __forceinline__ void bulk_wait_read_dyn(int pending) {   // pending in 0..4
     if (pending <= 0) bulk_wait_read<0>();
     else if (pending == 1) bulk_wait_read<1>();
-    else bulk_wait_read<2>();
+    else if (pending == 2) bulk_wait_read<2>();
+    else if (pending == 3) bulk_wait_read<3>();
+    else bulk_wait_read<4>();
 }
 // 16-byte async copy global -> shared through L2 (LDGSTS), for the grid tiles
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {

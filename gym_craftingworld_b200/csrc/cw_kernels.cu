@@ -482,10 +482,19 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
         dev->attr_set = true;
     }
     const bool needs_frame = (args.mode & M_RENDER) || args.goal_obs;
-    int F = env_tunable("CW_FRAME_BUFFERS", 2);
-    F = F < 2 ? 2 : (F > 4 ? 4 : F);
-    args.nbuf = F;
     args.bands_per_chunk = needs_frame ? pick_bands(cfg, env_tunable("CW_CHUNK_BYTES", 25 * 1024)) : 1;
+    // Ring depth F.  A launch of one or a few CTA waves (small batches) is fastest with F = 2 and 4 CTAs/SM; a persistent
+    // launch over many groups wants a deeper ring and larger groups (fewer CTAs/SM, the per-group step phase amortised
+    // over more worlds): measured on B200 at 21x21 (tools/sweep3.sh) F = 3 wins around 0.7 GB of frames per launch and
+    // F = 4 from ~1.3 GB up (0.90 -> 0.95 of the HBM roofline at 131072 worlds).  Multi-chunk frames keep F = 2.
+    int F = env_tunable("CW_FRAME_BUFFERS", 0);
+    if (F <= 0) {
+        const double frame_total = (double)st->n * 48.0 * cfg->H * cfg->W;
+        const bool single_chunk = args.bands_per_chunk >= cfg->H;
+        F = (!needs_frame || !single_chunk) ? 2 : (frame_total >= 1.2e9 ? 4 : (frame_total >= 0.6e9 ? 3 : 2));
+    }
+    F = F < 2 ? 2 : (F > 6 ? 6 : F);
+    args.nbuf = F;
     args.w_magic = (uint32_t)(0x100000000ull / (uint64_t)cfg->W) + 1u;
     args.first_split = env_tunable("CW_FIRST_SPLIT", 4);
     if (args.first_split < 1) args.first_split = 1;
