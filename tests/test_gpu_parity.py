@@ -408,3 +408,50 @@ def test_host_env_delta_transport_matches_oracle(cw, size, N, max_steps):
         assert np.array_equal(obs["desired_goal"], o_goal), f"host goal mirror diverged at step {k}"
     assert np.array_equal(env.stats(), ob.stats) and ob.stats[0] > 0
     env.close()
+
+
+def test_randomized_configurations_vs_oracle(cw):
+    """Fuzz: random grid sizes (3..40), batch sizes (incl. non-multiples of the group size), episode lengths, task
+    subsets, stacking, reward style and fixed pools; fused step + auto-reset + goal/init frames against the oracle."""
+    rng = np.random.RandomState(20260101)
+    names = cw.TASK_LIST
+    for trial in range(36):
+        size = int(rng.choice([3, 4, 5, 6, 7, 9, 11, 13, 16, 21, 24, 33, 40]))
+        N = int(rng.randint(1, 400))
+        max_steps = int(rng.randint(1, 14))
+        nsel = int(rng.randint(1, 10))
+        sel_idx = sorted(rng.choice(9, nsel, replace=False).tolist())
+        ntasks = int(rng.randint(1, nsel + 1))
+        stacking = bool(rng.randint(2))
+        subset = bool(rng.randint(2))
+        pool = int(rng.choice([0, 0, 3]))
+        seed = int(rng.randint(1 << 30))
+        base = int(rng.randint(1 << 20))
+        env = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, selected_tasks=[names[i] for i in sel_idx],
+                                         number_of_tasks=ntasks, stacking=stacking, reward_style=("s" if subset else None),
+                                         fixed_init_state=pool, seed=seed, env_id_base=base)
+        cfg = native.make_config(H=size, W=size, max_steps=max_steps, subset_reward=subset, stacking=stacking,
+                                 selected=tuple(sel_idx), number_of_tasks=ntasks)
+        ob = native.OracleBatch(cfg, N, seed=seed, env_id_base=base)
+        if pool:                                       # the C oracle keeps raw pointers: the arrays must outlive the trial
+            pool_g, pool_a = env._fixed_grid.cpu().numpy().copy(), env._fixed_agent.cpu().numpy().astype(np.uint32)
+            native.set_fixed_pool(pool_g, pool_a)
+        try:
+            env.reset()
+            o_goal = ob.reset(with_goal=True)
+            o_obs = ob.render()
+            new_goal = np.zeros_like(o_goal)
+            K = int(rng.randint(5, 30))
+            for k in range(K):
+                a = rng.randint(0, 6, N).astype(np.uint8)
+                _, reward, done, _ = env.step(a)
+                o_reward, o_done = ob.step_full(a, auto_reset=True, obs=o_obs, goal_obs=new_goal)
+                o_goal[o_done == 1] = new_goal[o_done == 1]
+                where = f"trial {trial} size {size} N {N} max_steps {max_steps} step {k}"
+                assert np.array_equal(reward.cpu().numpy(), o_reward) and np.array_equal(done.cpu().numpy(), o_done.astype(bool)), where
+            assert_env_equals_oracle(env, ob, where)
+            assert np.array_equal(env.obs.cpu().numpy(), o_obs), where
+            assert np.array_equal(env.desired_goal.cpu().numpy(), o_goal), where
+            assert np.array_equal(env.stats.cpu().numpy(), ob.stats), where
+        finally:
+            native.set_fixed_pool(None)
