@@ -201,39 +201,62 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
     uint32_t des = 0;
     uint32_t cells[9];
     bool sampled = false;
-    // ---- speculative lane-parallel sampling -------------------------------------------------------------------
-    // The serial algorithm below consumes exactly 1 + n_tasks + 9 draws unless a Lemire draw lands in the rejection
-    // zone or two cells collide.  Fetch all of them at once (lane i = i-th draw of its group); if NO lane sees
-    // "low word < n" (a superset of the rejection zone) and no two cells are equal, the results are by
-    // construction those of the serial loop; otherwise rewind the stream and run the serial loop.
+    // ---- lane-parallel sampling with exact redraw semantics --------------------------------------------------------
+    // The serial algorithm (the fallback below; spec: oracle/compact.py) walks the stream: draw i+1 follows the last draw
+    // used by draw i, and a draw is repeated when it lands in Lemire's rejection zone or (placement) on an occupied cell.
+    // Here lane i evaluates position i from stream offset (base + i + shift_i); the FIRST violating position k is exactly
+    // where the serial loop would redraw, so all positions >= k move one draw forward and the round repeats.  Rounds are
+    // rare (8 % of resets at 21x21 need one), every round is a handful of shuffles instead of a dependent loop.
     if (st.n_fixed == 0) {
-        auto fetch = [&](int d) {                                // draw d (per lane) of the buffered block
+        auto fetch = [&](int d) {                                // draw d (per lane) of the buffered 128-draw block
             const int src = d >> 2, sl = d & 3;
             const uint32_t a0 = __shfl_sync(0xffffffffu, rng.w0, src), a1 = __shfl_sync(0xffffffffu, rng.w1, src);
             const uint32_t a2 = __shfl_sync(0xffffffffu, rng.w2, src), a3 = __shfl_sync(0xffffffffu, rng.w3, src);
             return sl == 0 ? a0 : (sl == 1 ? a1 : (sl == 2 ? a2 : a3));
         };
-        bool anomaly = false;
+        bool ok = true;
         int consumed = 0, ntask = 1;
-        if (cfg.stacking) {                                      // ray.py:169
-            const uint64_t m = (uint64_t)fetch(0) * (uint32_t)cfg.number_of_tasks;
-            anomaly |= (uint32_t)m < (uint32_t)cfg.number_of_tasks;
-            ntask = (int)(m >> 32) + 1;
-            consumed = 1;
+        if (cfg.stacking) {                                      // ray.py:169 (warp-uniform)
+            const uint32_t nn = (uint32_t)cfg.number_of_tasks, thresh = (0u - nn) % nn;
+            for (;;) {
+                const uint64_t m = (uint64_t)fetch(consumed++) * nn;
+                if ((uint32_t)m >= thresh) { ntask = (int)(m >> 32) + 1; break; }
+                if (consumed > 32) { ok = false; break; }
+            }
         }
         const int li = lane < 8 ? lane : 8;
-        const uint32_t nsel_i = (uint32_t)(cfg.n_selected - li);  // Fisher-Yates: j_i = i + uniform(n_selected - i)
-        const uint64_t mf = (uint64_t)fetch(consumed + li) * nsel_i;
-        anomaly |= (lane < ntask) && ((uint32_t)mf < nsel_i);
-        const int j_mine = li + (int)(mf >> 32);
-        consumed += ntask;
-        const uint64_t mc = (uint64_t)fetch(consumed + li) * ncell;  // placement: cell_i = uniform(H*W), ray.py:605-613
-        const uint32_t cell_mine = (uint32_t)(mc >> 32);
-        anomaly |= (lane < 9) && ((uint32_t)mc < ncell);
-        const uint32_t twins = __match_any_sync(0xffffffffu, lane < 9 ? cell_mine : 0x80000000u + (uint32_t)lane);
-        anomaly |= (twins & ~(1u << lane)) != 0;
-        consumed += 9;
-        if (!__any_sync(0xffffffffu, anomaly)) {
+        int j_mine = 0;
+        if (ok) {                                                // Fisher-Yates: j_i = i + uniform(n_selected - i)
+            const uint32_t nsel_i = lane < ntask ? (uint32_t)(cfg.n_selected - li) : 1u;
+            const uint32_t thresh_i = (0u - nsel_i) % nsel_i;
+            int shift = 0;
+            for (;;) {
+                const uint64_t mf = (uint64_t)fetch(consumed + li + shift) * nsel_i;
+                j_mine = li + (int)(mf >> 32);
+                const uint32_t bad = __ballot_sync(0xffffffffu, lane < ntask && (uint32_t)mf < thresh_i);
+                if (!bad) break;
+                if (lane >= __ffs(bad) - 1) shift++;
+                if (consumed + 9 + __shfl_sync(0xffffffffu, shift, 8) >= 100) { ok = false; break; }   // stay inside the block
+            }
+            consumed += ntask + __shfl_sync(0xffffffffu, shift, ntask - 1);
+        }
+        uint32_t cell_mine = 0;
+        if (ok) {                                                // placement: 9 distinct uniform cells, ray.py:605-613
+            const uint32_t thresh_c = (0u - ncell) % ncell;
+            int shift = 0;
+            for (;;) {
+                const uint64_t mc = (uint64_t)fetch(consumed + li + shift) * ncell;
+                cell_mine = (uint32_t)(mc >> 32);
+                const uint32_t twins = __match_any_sync(0xffffffffu, lane < 9 ? cell_mine : 0x80000000u + (uint32_t)lane);
+                const bool viol = lane < 9 && ((uint32_t)mc < thresh_c || (twins & ((1u << lane) - 1u)) != 0);
+                const uint32_t bad = __ballot_sync(0xffffffffu, viol);
+                if (!bad) break;
+                if (lane >= __ffs(bad) - 1) shift++;
+                if (consumed + 9 + __shfl_sync(0xffffffffu, shift, 8) >= 127) { ok = false; break; }
+            }
+            consumed += 9 + __shfl_sync(0xffffffffu, shift, 8);
+        }
+        if (ok) {
             for (int i = 0; i < ntask; i++) {
                 const int j = __shfl_sync(0xffffffffu, j_mine, i);
                 const uint64_t vi = (perm >> (4 * i)) & 15, vj = (perm >> (4 * j)) & 15;
@@ -245,7 +268,7 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
             rng.pos = consumed;
             sampled = true;
         } else {
-            rng.pos = 0;                                         // rewind: the buffered block is still valid
+            rng.pos = 0;                                         // ultra-rare: rewind and walk the stream serially
         }
     }
     if (!sampled) {
