@@ -222,7 +222,7 @@ def run_ours(args):
         dense_worlds(env, torch, 99 + rank)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     tape = torch.randint(0, 6, (TAPE, N), generator=gen, device=dev, dtype=torch.uint8)
-    reducer = cw.StatsReducer(env.stats, every=TAPE, inline=os.environ.get("CW_STATS_INLINE", "0") == "1") if world > 1 else None
+    reducer = cw.StatsReducer(env.stats_raw, every=TAPE, inline=os.environ.get("CW_STATS_INLINE", "0") == "1") if world > 1 else None
 
     def barrier():
         if world > 1:

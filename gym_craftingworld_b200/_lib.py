@@ -11,6 +11,7 @@ from . import build as _build
 
 ABI_VERSION = 1
 STATS_LEN = 24
+STATS_REPLICAS = 16
 MAX_SIDE = 64
 F_AUTO_RESET = 1
 F_DELTA_TRANSPORT = 2

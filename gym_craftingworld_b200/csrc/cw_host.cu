@@ -196,10 +196,10 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
     TRY(cudaMalloc(&e->d_reward, n * 5));                       // [reward int32 x n][done uint8 x n], one block
     if (!rc) e->d_done = reinterpret_cast<uint8_t*>(e->d_reward) + n * 4;
     TRY(cudaMalloc(&e->d_obs, (size_t)n * e->frame_bytes)); TRY(cudaMalloc(&e->d_goal_obs, (size_t)n * e->frame_bytes));
-    TRY(cudaMalloc(&e->d_stats, CW_STATS_LEN * 8));
+    TRY(cudaMalloc(&e->d_stats, CW_STATS_REPLICAS * CW_STATS_LEN * 8));
     TRY(cudaMallocHost(&e->h_actions, n)); TRY(cudaMallocHost(&e->h_reward, n * 5));
     if (!rc) e->h_done = reinterpret_cast<uint8_t*>(e->h_reward) + n * 4;
-    TRY(cudaMallocHost(&e->h_stats, CW_STATS_LEN * 8));
+    TRY(cudaMallocHost(&e->h_stats, CW_STATS_REPLICAS * CW_STATS_LEN * 8));
     if (flags & CW_F_DELTA_TRANSPORT) {
         TRY(cudaMallocHost(&e->h_delta, n * sizeof(uint4)));
         TRY(cudaMallocHost(&e->h_fresh, n * CW_FRESH_WORDS * sizeof(uint32_t)));
@@ -216,7 +216,7 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
         TRY(cudaMemset(e->st.grid, 0, gb)); TRY(cudaMemset(e->st.init_grid, 0, gb));
         TRY(cudaMemset(e->st.agent, 0, n * 4)); TRY(cudaMemset(e->st.goal, 0, n * 4));
         TRY(cudaMemset(e->st.t, 0, n * 4)); TRY(cudaMemset(e->st.episode, 0, n * 4));
-        TRY(cudaMemset(e->d_stats, 0, CW_STATS_LEN * 8));
+        TRY(cudaMemset(e->d_stats, 0, CW_STATS_REPLICAS * CW_STATS_LEN * 8));
         TRY(cudaDeviceSynchronize());
     }
 #undef TRY
@@ -365,9 +365,13 @@ int cw_host_stats(CwHostEnv* e, int64_t* stats_host) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     if (!stats_host) return CW_E_NULLPTR;
     CK(cudaSetDevice(e->device));
-    CK(cudaMemcpyAsync(e->h_stats, e->d_stats, CW_STATS_LEN * 8, cudaMemcpyDeviceToHost, e->streams[0]));
+    CK(cudaMemcpyAsync(e->h_stats, e->d_stats, CW_STATS_REPLICAS * CW_STATS_LEN * 8, cudaMemcpyDeviceToHost, e->streams[0]));
     CK(cudaStreamSynchronize(e->streams[0]));
-    memcpy(stats_host, e->h_stats, CW_STATS_LEN * 8);
+    for (int k = 0; k < CW_STATS_LEN; k++) {                     // sum the replicas
+        int64_t v = 0;
+        for (int r = 0; r < CW_STATS_REPLICAS; r++) v += e->h_stats[r * CW_STATS_LEN + k];
+        stats_host[k] = v;
+    }
     return 0;
 }
 

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     if (args.done) args.done[e] = dn ? 1 : 0;
                     if (dn && (mode & M_AUTO_RESET)) {
                         flag |= FL_PENDING;
-                        if (args.stats) stats_add(cfg, args.stats, goal, t, rew);
+                        if (args.stats) stats_add(cfg, args.stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
                     } else {
                         st.agent[e] = agent; st.goal[e] = goal; st.t[e] = t;
                         if (args.delta)                           // one 16-byte store (possibly into mapped host memory)
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
             const int rew = step_core(cfg, g, ig, agent, goal, t, a, dn, wcell, wval);
             if (reward) reward[(size_t)k * st.n + n] = rew;
             if (done) done[(size_t)k * st.n + n] = dn ? 1 : 0;
-            if (dn && (flags & CW_F_AUTO_RESET) && stats) stats_add(cfg, stats, goal, t, rew);
+            if (dn && (flags & CW_F_AUTO_RESET) && stats) stats_add(cfg, stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
         }
         if (flags & CW_F_AUTO_RESET) {                            // finished worlds are re-seeded by the whole warp
             uint32_t m = __ballot_sync(0xffffffffu, valid && dn);

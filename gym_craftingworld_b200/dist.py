@@ -55,6 +55,11 @@ class StatsReducer:
             self.global_stats.copy_(self.stats, non_blocking=True)
             dist.all_reduce(self.global_stats, op=dist.ReduceOp.SUM, group=self.group)
 
+    def total(self) -> torch.Tensor:
+        """Global statistics vector; sums the device replicas when the reducer was given ``env.stats_raw``."""
+        g = self.wait()
+        return g.sum(dim=0) if g.dim() == 2 else g
+
     def wait(self) -> torch.Tensor:
         if self._work is not None:
             self._work.wait()

@@ -188,7 +188,7 @@ class BatchedCraftingWorldEnv:
         self.reward = torch.zeros(N, dtype=torch.int32, device=dev)
         self._done_u8 = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.done = self._done_u8.view(torch.bool)
-        self.stats = torch.zeros(_lib.STATS_LEN, dtype=torch.int64, device=dev)
+        self.stats_raw = torch.zeros((_lib.STATS_REPLICAS, _lib.STATS_LEN), dtype=torch.int64, device=dev)
         self.frame_shape = (N, ph, pw, 3)
         self._obs_ring, self._ring_pos = [], 0
         self.obs = self.desired_goal = self.init_obs = None
@@ -253,6 +253,11 @@ class BatchedCraftingWorldEnv:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # ---- reference-style attributes ------------------------------------------------------------------
+    @property
+    def stats(self):
+        """``int64[24]`` finished-episode statistics of this rank (the device keeps 16 replicas to spread the atomics)."""
+        return self.stats_raw.sum(dim=0)
+
     @property
     def achieved_mask(self):
         return self.goal & 0xFFFF
@@ -329,7 +334,7 @@ class BatchedCraftingWorldEnv:
         return None if t is None else t.data_ptr()
 
     def _stats_ptr(self):
-        return self.stats.data_ptr() if self.collect_stats else None
+        return self.stats_raw.data_ptr() if self.collect_stats else None
 
     # ---- reset / step ------------------------------------------------------------------------------------
     def reset(self, mask=None):

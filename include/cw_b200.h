@@ -26,7 +26,7 @@
  *   t                int32 [N]               step_num (ray.py:203, 309)
  *   episode          uint32[N]               resets performed so far = Philox counter word of the next reset
  *   obs, goal_obs    uint8 [N][4H][4W][3]    RGB frames (ray.py:442-486); goal_obs = imagine_obs (ray.py:220-299)
- *   stats            int64 [CW_STATS_LEN]    0 episodes 1 successes 2 return_sum 3 length_sum
+ *   stats            int64 [CW_STATS_REPLICAS][CW_STATS_LEN]  (sum over replicas:) 0 episodes 1 successes 2 return_sum 3 length_sum
  *                                            4..12 achieved-skill counts 13..21 desired-skill counts (finished eps)
  */
 #ifndef CW_B200_H
@@ -40,6 +40,8 @@ extern "C" {
 
 #define CW_ABI_VERSION 1
 #define CW_STATS_LEN 24
+#define CW_STATS_REPLICAS 16 /* the stats buffer is int64[CW_STATS_REPLICAS][CW_STATS_LEN]: finished episodes are added to
+                                replica (block index % 16) so same-address atomics do not serialise; consumers sum the replicas */
 #define CW_MAX_SIDE 64 /* H, W <= 64 (cell_stride <= 4096) */
 #define CW_FRESH_WORDS 18 /* delta transport: uint32 words of a re-seeded world's sparse record (see cw_step_delta) */
 
