@@ -12,6 +12,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "cw_b200.h"
 #include "cw_device.cuh"
 
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
 // observation_vector (ray.py:94-98, 605-613): one 32-bit word (4 of the 12 channel bytes of a cell) per thread
 __global__ void __launch_bounds__(256) cw_onehot_kernel(const CwConfig cfg, const uint8_t* __restrict__ grid,
                                                         const uint32_t* __restrict__ agent, uint32_t* __restrict__ out,
-                                                        int64_t n_words, uint32_t hw3_magic_unused) {
+                                                        int64_t n_words) {
     const int HW = cfg.H * cfg.W;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
         const int64_t cellg = w / 3;
@@ -400,6 +402,7 @@ __global__ void __launch_bounds__(256) cw_render_alt_kernel(const CwConfig cfg, 
 struct OccEntry { size_t smem; int per_sm; };
 struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool attr_set = false; int max_dyn = 0; int n_occ = 0; OccEntry occ[64]; };
 static DeviceInfo g_dev[64];
+static std::mutex g_dev_mu;   // guards the per-device attribute / occupancy cache (entry points may be called from several host threads)
 
 static int device_info(DeviceInfo** out) {
     int dev = 0;
@@ -407,6 +410,7 @@ static int device_info(DeviceInfo** out) {
     if (e != cudaSuccess) return (int)e;
     if (dev < 0 || dev >= 64) return CW_E_BADCONFIG;
     DeviceInfo& d = g_dev[dev];
+    std::lock_guard<std::mutex> lk(g_dev_mu);
     if (!d.ok) {
         e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
@@ -470,6 +474,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     if (rc) return rc;
     if (st->n <= 0) return 0;
     auto kern = cw_env_kernel;
+    std::unique_lock<std::mutex> lk(g_dev_mu);
     if (!dev->attr_set) {   // once per device: allow any dynamic size up to the opt-in maximum, prefer shared memory
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, kern);
@@ -525,6 +530,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
         const int64_t cost = waves * G + waves;                  // + a fixed per-wave cost (load / step latency)
         if (bestG == 0 || cost < best_cost || (cost == best_cost && G > bestG)) { bestG = G; best_cost = cost; best_per_sm = per_sm; }
     }
+    lk.unlock();
     if (bestG == 0) return CW_E_BADCONFIG;
     args.group = bestG;
     const size_t smem = 3 * (size_t)bestG * cfg->cell_stride + ring;
@@ -664,7 +670,7 @@ int cw_onehot(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, u
     int64_t blocks = (n_words + 255) / 256;
     const int64_t cap = (int64_t)dev->sms * 16;
     if (blocks > cap) blocks = cap;
-    cw_onehot_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, grid, agent, (uint32_t*)onehot, n_words, 0);
+    cw_onehot_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, grid, agent, (uint32_t*)onehot, n_words);
     return (int)cudaGetLastError();
 }
 
