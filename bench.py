@@ -237,40 +237,53 @@ def run_ours(args):
             env.step(tape[k % TAPE])
         torch.cuda.synchronize()
 
-        def capture(nsteps):
+        chain = pixels and not args.no_chain
+        if chain:
+            env.step(tape[0], chain_pos=0)                       # warm the chained launch path outside the capture
+
+        def capture(nsteps, chained):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
                 for k in range(nsteps):
-                    env.step(tape[k])
+                    env.step(tape[k], chain_pos=k if chained else None)
             return g
-        n_full, rem = divmod(K, TAPE)
-        g_full = capture(TAPE) if n_full else None
-        g_rem = capture(rem) if rem else None
-        for g in (g_full, g_rem):                                # one untimed replay each (extra warm-up)
-            if g is not None:
-                g.replay()
-        torch.cuda.synchronize()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record(stream)
-        for _ in range(n_full):
-            g_full.replay()
+
+        def timed(chained):
+            """exactly K steps replayed from graphs of TAPE steps; device time between two events, max over ranks"""
+            n_full, rem = divmod(K, TAPE)
+            g_full = capture(TAPE, chained) if n_full else None
+            g_rem = capture(rem, chained) if rem else None
+            for g in (g_full, g_rem):                            # one untimed replay each (extra warm-up)
+                if g is not None:
+                    g.replay()
+            torch.cuda.synchronize()
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            ev0.record(stream)
+            for _ in range(n_full):
+                g_full.replay()
+                if reducer is not None:
+                    reducer.reduce_async()                       # every 128 steps, on a side stream
+            if g_rem is not None:
+                g_rem.replay()
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            w1 = time.perf_counter()
+            barrier()
             if reducer is not None:
-                reducer.reduce_async()                           # every 128 steps, on a side stream
-        if g_rem is not None:
-            g_rem.replay()
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        barrier()
-        if reducer is not None:
-            reducer.wait()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        tmax = torch.tensor([ms], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
+                reducer.wait()
+            t_ms = ev0.elapsed_time(ev1)
+            if world > 1:
+                tmax = torch.tensor([t_ms], device=dev)
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                t_ms = float(tmax.item())
+            return t_ms, w0, w1
+
+        ms_unchained = None
+        if chain and not args.no_unchained:                      # the same K steps as independent launches, for comparison
+            ms_unchained, _, _ = timed(False)
+        ms, t0, t1 = timed(chain)
     stats_local = env.episode_stats()
 
     # ---- end to end through the host-buffer C entry points --------------------------------------------------
@@ -328,12 +341,18 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "envs_per_gpu": N, "grid": f"{size}x{size}", "obs": wl["obs"],
                        "actions": "uniform iid over 6 actions, pre-generated uint8[128,N] tape on device, cycled",
-                       "launch": f"CUDA graphs of {TAPE} steps, one fused launch per step",
+                       "launch": (f"CUDA graphs of {TAPE} steps, one fused launch per step"
+                                  + ("; launches chained by per-group dataflow (cw_step_render_chained: open-loop action tape, step i+1 "
+                                     "overlaps the draining frame stores of step i; results identical)" if chain else "")),
                        "l2": (f"frames written round-robin into {ring} buffers = {ring * N * frame_bytes / 1e6:.0f} MB > 126 MB L2 "
                               "(inputs larger than L2; no flush needed)") if pixels else "state 65536 x ~0.9 KB; step kernel is latency bound",
                        "parallelism": f"dp{world} (worlds sharded by global id, no data-path collective)"},
             "clocks": sampler.summary(t0, t1, t_load0) if sampler else None,
             "gpu_launches": K,
+            "unchained": ({"value": N * world * K / (ms_unchained / 1e3), "unit": UNIT, "ms_per_step": ms_unchained / K,
+                           "roofline_frac": B * N / (ms_unchained / 1e3 / K) / 1e9 / peak,
+                           "note": "the same K steps as independent (whole-grid dependent, PDL) launches: what a closed loop "
+                                   "with a policy between the steps can use"} if ms_unchained else None),
             "e2e": e2e or None,
             "roofline": {"bound": "hbm", "kernel": "cw_env_kernel" if pixels else "cw_step_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
@@ -406,6 +425,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="shorter CPU baseline / e2e legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-chain", action="store_true", help="independent launches instead of chained ones")
+    ap.add_argument("--no-unchained", action="store_true", help="skip the comparison leg with independent launches")
     ap.add_argument("--no-stats", action="store_true", help="experiment: do not accumulate episode statistics")
     ap.add_argument("--no-goal-images", action="store_true", help="experiment: skip imagine_obs / goal + init frames")
     ap.add_argument("--max-steps", type=int, default=300, help="experiment: episode length (reference default 300)")

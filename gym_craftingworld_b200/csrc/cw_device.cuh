@@ -116,7 +116,7 @@ __device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restric
         int here = g[cell];
         const int T = g[ncell];
         int ih = 0, ihn = 0;
-        if (h != 0) { ih = ig[cell]; ihn = ig[ncell]; }
+        if (h != 0) { ih = __ldcg(ig + cell); ihn = __ldcg(ig + ncell); }   // L2: a co-resident chained launch may have re-seeded it
         int old = EMPTY;  // EMPTY == "None": matches no predicate below (ray.py:655 uses 100)
         bool moved = ncell != cell;                                              // ray.py:395-396
         const bool blocked = ((T == ROCK) & (h != HAMMER)) | ((T == TREE) & (h != AXE));   // ray.py:401-405
@@ -606,6 +606,7 @@ __device__ __forceinline__ void compose_bands(const CwConfig& cfg, const uint8_t
 // ---- TMA bulk store (shared::cta -> global), sm_90+ : SASS UBLKCP ---------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     uint64_t pol;   // streaming frames: ask L2 to evict them first (measured A/B: +2.9% at 4096 worlds, +0.5% at 131072)
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));

@@ -42,7 +42,36 @@ struct EnvArgs {
     int bands_per_chunk;
     int first_split;         // the first frame of a launch is stored in this many pieces (earlier first store)
     uint32_t w_magic;        // floor(2^32 / W) + 1
+    // chained launches (cw_step_render_chained): per-group dataflow instead of a whole-grid dependency
+    uint32_t* chain;         // [CW_CHAIN_MAX_POS] finished-CTA counters per chain position, then one epoch word per group
+    int chain_pos;           // position of this launch in its chain (0 = ordinary launch that opens a chain)
+    int chain_ring;          // the chain's frame buffers rotate with this period (>= 1)
 };
+
+// ---- chained launches: acquire / release on the chain words (gpu scope), bounded spins --------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p >= want.  A chain that was set up wrongly must not hang the GPU: after 2 s the kernel traps.
+__device__ __forceinline__ void chain_wait_ge(const uint32_t* p, uint32_t want) {
+    if (ld_acquire_gpu(p) >= want) return;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        __nanosleep(64);
+        if (ld_acquire_gpu(p) >= want) return;
+        if (global_timer_ns() - t0 > 2000000000ull) __trap();
+    }
+}
 
 #ifdef CW_TIMING
 __device__ unsigned long long* g_dbg = nullptr;   // [CTA][16] globaltimer stamps (experiments only)
@@ -75,6 +104,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32], s_ep[32], s_rew[32];
     __shared__ uint32_t s_flag[32];
     __shared__ uint32_t s_obj[8];
+    __shared__ uint32_t s_anypend;
 
     const int H = cfg.H, W = cfg.W, cs = cfg.cell_stride;
     const int G = args.group, F = args.nbuf, mode = args.mode;
@@ -90,13 +120,25 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     const uint8_t* grid_in = args.rgrid ? args.rgrid : st.grid;
     const uint32_t* agent_in = args.ragent ? args.ragent : st.agent;
     const int64_t ngroups = (st.n + G - 1) / G;
+    // Chained launch (cw_step_render_chained, position > 0): the previous launch in the stream is the same kernel on the
+    // same worlds, one chain position earlier.  Instead of waiting for that whole grid (and for its frame stores to
+    // drain), a CTA waits per GROUP for the predecessor's state of exactly the worlds it is about to step (epoch word,
+    // release/acquire), and -- before its first frame store -- for the launch that last wrote the same frame buffer
+    // (finished-CTA counter, `chain_ring` positions back).  griddepcontrol.wait moves to the END of the kernel, so
+    // grids still COMPLETE in stream order.
+    const uint32_t cpos = (uint32_t)args.chain_pos;
+    const bool chained = args.chain != nullptr;
+    const bool chain_follow = chained && cpos > 0;
+    uint32_t* const c_fin = args.chain;
+    uint32_t* const c_epoch = args.chain + CW_CHAIN_MAX_POS;
+    bool fin_wait_pending = chained && args.chain_pos >= args.chain_ring;
 
     // Programmatic dependent launch: let the next launch in the stream start its prologue now, and do not touch
     // anything the previous launch wrote (state, frames) until it has fully completed.
     CW_STAMP(0);
     pdl_launch_dependents();
     if (tid < 9) s_lut[tid] = kColorLUT[tid];
-    pdl_wait();
+    if (!chain_follow) pdl_wait();
     CW_STAMP(1);
 
     // tile + scalar prefetch of group `g` (tiles -> stage `sgi`; scalars -> registers of warp 0)
@@ -104,18 +146,19 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     int p_t = 0, p_a = 6, p_forced = 0;
     auto prefetch = [&](int64_t g, int sgi) {
         if (g < ngroups) {
+            if (chain_follow) chain_wait_ge(c_epoch + g, cpos);   // every thread acquires: its loads below are ordered after
             const int64_t e0 = g * G;
             const int cnt = (int)min((int64_t)G, st.n - e0);
             const uint8_t* src = grid_in + e0 * cs;
             uint8_t* dst = tiles + (size_t)sgi * G * cs;
             for (int i = tid; i < cnt * nchunk16; i += kEnvThreads) cp_async16(dst + 16 * i, src + 16 * i);
-            if (tid < cnt) {
+            if (tid < cnt) {                                      // L2 loads (.cg): state may come from a co-resident launch
                 const int64_t e = e0 + tid;
-                p_agent = agent_in[e];
-                if (mode & (M_STEP | M_IMAGINE_ONLY)) p_goal = st.goal[e];
-                if (mode & M_STEP) { p_t = st.t[e]; p_a = args.actions[e]; }
+                p_agent = __ldcg(agent_in + e);
+                if (mode & (M_STEP | M_IMAGINE_ONLY)) p_goal = __ldcg(st.goal + e);
+                if (mode & M_STEP) { p_t = __ldcg(st.t + e); p_a = args.actions[e]; }
                 if (mode & M_FORCE_RESET) p_forced = (!args.mask || args.mask[e]) ? 1 : 0;
-                if (mode & (M_AUTO_RESET | M_FORCE_RESET | M_IMAGINE_ONLY)) p_ep = st.episode[e];
+                if (mode & (M_AUTO_RESET | M_FORCE_RESET | M_IMAGINE_ONLY)) p_ep = __ldcg(st.episode + e);
             }
         }
         cp_async_commit();
@@ -133,6 +176,11 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
             if (tid == 0) bulk_wait_read_dyn(F - 2);              // frees the slot the NEXT chunk composes into
             bar_sync(BAR_COMPOSE, kComposeThreads);
             if (tid == 0) {
+                if (fin_wait_pending) {                           // the launch that last wrote this frame buffer has completed
+                    chain_wait_ge(c_fin + (cpos - (uint32_t)args.chain_ring), gridDim.x);
+                    fence_proxy_async_all();
+                    fin_wait_pending = false;
+                }
                 bulk_store(dst + (size_t)band0 * band_bytes, fb, band_bytes * nb);
                 if (dst2) bulk_store(dst2 + (size_t)band0 * band_bytes, fb, band_bytes * nb);
                 bulk_commit();
@@ -184,12 +232,18 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                 }
             }
             if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; s_ep[lane] = c_ep; s_rew[lane] = rew_stash; }
+            const uint32_t pend = __ballot_sync(0xffffffffu, (flag & FL_PENDING) != 0);
+            if (lane == 0) s_anypend = pend;
         }
         __syncthreads();
         CW_STAMP(3);
         if (!composer) {
             // ---- R: the reset warp works through the pending worlds, then arrives on BAR_RESET_DONE -----------------
             const int lane = tid - kComposeThreads;
+            // chained: publish this group's state for the next chain position.  Without a re-seeded world the state is
+            // final right here (warp 0 wrote it before the barrier); otherwise thread 0 publishes after the re-seeded
+            // worlds' frames (goal / init frames have no ring) have been written completely.
+            if (chained && s_anypend == 0 && lane == 0) { __threadfence(); st_release_gpu(c_epoch + gi, cpos + 1u); }
             for (int i = 0; i < G; i++) {
                 uint32_t flag = s_flag[i];
                 if (!(flag & FL_PENDING)) continue;
@@ -281,13 +335,18 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     emit_frame(gt + i * cs, s_agent[i], args.obs + off, ((flag & FL_FRESH) && args.init_obs) ? args.init_obs + off : nullptr,
                                args.bands_per_chunk);
             }
+            if (chained && s_anypend != 0 && tid == 0) { bulk_wait_all(); __threadfence(); st_release_gpu(c_epoch + gi, cpos + 1u); }
         }
         CW_STAMP(6);
         __syncthreads();                                          // tiles / s_* of this stage are rewritten next
         stage ^= 1;
     }
     cp_async_wait<0>();
-    if (tid == 0) bulk_wait_all();
+    if (tid == 0) {
+        bulk_wait_all();
+        if (chained) { __threadfence(); atomicAdd(c_fin + cpos, 1u); }   // this CTA's frames of chain position cpos are complete
+    }
+    if (chain_follow) pdl_wait();                                 // do not COMPLETE before the predecessor grid has
     CW_STAMP(7);
 }
 
@@ -537,6 +596,10 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     int64_t blocks = (int64_t)dev->sms * best_per_sm;
     const int64_t groups = (st->n + bestG - 1) / bestG;
     if (blocks > groups) blocks = groups;
+    if (args.chain && args.chain_pos == 0) {                      // a chain opens: clear its counters and epoch words
+        cudaError_t me = cudaMemsetAsync(args.chain, 0, sizeof(uint32_t) * (size_t)(CW_CHAIN_MAX_POS + st->n), stream);
+        if (me != cudaSuccess) return (int)me;
+    }
     cudaError_t le = launch_pdl(kern, dim3((unsigned)blocks), dim3(kEnvThreads), smem, stream, *cfg, *st, args);
     return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
@@ -631,6 +694,24 @@ int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* action
     a.actions = actions; a.reward = reward; a.done = done; a.obs = obs; a.goal_obs = goal_obs; a.init_obs = init_obs;
     a.stats = (unsigned long long*)stats;
     a.mode = M_STEP | (obs ? M_RENDER : 0) | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
+    return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
+}
+
+int cw_step_render_chained(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
+                           uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, uint32_t* chain,
+                           int chain_pos, int obs_ring, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    rc = check_state(st); if (rc) return rc;
+    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
+    if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
+    if (chain_pos < 0 || chain_pos >= CW_CHAIN_MAX_POS || obs_ring < 1) return CW_E_BADCONFIG;
+    if (st->n == 0) return 0;
+    if (!actions || !reward || !done || !obs || !chain) return CW_E_NULLPTR;
+    EnvArgs a = {};
+    a.actions = actions; a.reward = reward; a.done = done; a.obs = obs; a.goal_obs = goal_obs; a.init_obs = init_obs;
+    a.stats = (unsigned long long*)stats;
+    a.mode = M_STEP | M_RENDER | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
+    a.chain = chain; a.chain_pos = chain_pos; a.chain_ring = obs_ring;
     return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
 }
 

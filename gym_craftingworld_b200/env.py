@@ -204,6 +204,7 @@ class BatchedCraftingWorldEnv:
             self.goal_agent = torch.zeros(N, dtype=torch.int32, device=dev)
             self.init_agent = torch.zeros(N, dtype=torch.int32, device=dev)
         self._obs_version = 0
+        self._chain = None                        # chain words of cw_step_render_chained (allocated on first use)
         self._fixed_grid = self._fixed_agent = None
         self._seed = None
         self._state = _lib.CwState()
@@ -363,18 +364,37 @@ class BatchedCraftingWorldEnv:
             a = a.to(torch.uint8)
         return a.contiguous()
 
-    def step(self, actions):
+    def step(self, actions, chain_pos=None):
         """``step`` (``ray.py:301-378``) for all worlds: ``(obs dict, reward int32[N], done bool[N], info)``.
-        One kernel launch; asynchronous on the current stream (CUDA-graph capturable)."""
+        One kernel launch; asynchronous on the current stream (CUDA-graph capturable).
+
+        ``chain_pos`` (pixel observations only) declares an OPEN-LOOP run of steps -- an action tape that exists before
+        the run starts, e.g. the K steps captured into one CUDA graph: pass 0, 1, 2, ... for consecutive calls with
+        nothing else enqueued on the stream in between.  Launch ``i > 0`` then follows launch ``i - 1`` by per-group
+        dataflow (``cw_step_render_chained``) instead of waiting for its whole grid, so its work overlaps the draining
+        frame stores of the previous step.  Results are identical; a closed loop (actions computed from the previous
+        observation) must use ``chain_pos=None``."""
         a = self._as_actions(actions)
         if a.shape != (self.num_envs,):
             raise ValueError(f"actions must have shape ({self.num_envs},), got {tuple(a.shape)}")
+        if chain_pos is not None and (self.obs_mode != "pixels" or not 0 <= int(chain_pos) < _lib.CHAIN_MAX_POS):
+            raise ValueError(f"chain_pos needs obs_mode='pixels' and 0 <= chain_pos < {_lib.CHAIN_MAX_POS}")
         flags = _lib.F_AUTO_RESET if self.auto_reset else 0
         with torch.cuda.device(self.device):
             if self.obs_mode == "pixels":
                 if len(self._obs_ring) > 1:
                     self._ring_pos = (self._ring_pos + 1) % len(self._obs_ring)
                     self.obs = self._obs_ring[self._ring_pos]
+                if chain_pos is not None:
+                    if self._chain is None:
+                        self._chain = torch.zeros(_lib.CHAIN_MAX_POS + self.num_envs, dtype=torch.int32, device=self.device)
+                    rc = self._lib.cw_step_render_chained(
+                        C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(), self._done_u8.data_ptr(),
+                        self.obs.data_ptr(), self._ptr(self.desired_goal), self._ptr(self.init_obs), self._stats_ptr(), flags,
+                        self._chain.data_ptr(), int(chain_pos), len(self._obs_ring), self._stream())
+                    _lib.check(rc, "cw_step_render_chained")
+                    self._obs_version += 1
+                    return self._observation(), self.reward, self.done, self._info
                 rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
                                               self._done_u8.data_ptr(), self.obs.data_ptr(), self._ptr(self.desired_goal),
                                               self._ptr(self.init_obs), self._stats_ptr(), flags, self._stream())

@@ -38,11 +38,12 @@
 extern "C" {
 #endif
 
-#define CW_ABI_VERSION 1
+#define CW_ABI_VERSION 2
 #define CW_STATS_LEN 24
 #define CW_STATS_REPLICAS 16 /* the stats buffer is int64[CW_STATS_REPLICAS][CW_STATS_LEN]: finished episodes are added to
                                 replica (block index % 16) so same-address atomics do not serialise; consumers sum the replicas */
 #define CW_MAX_SIDE 64 /* H, W <= 64 (cell_stride <= 4096) */
+#define CW_CHAIN_MAX_POS 1024 /* chained launches: positions 0..1023; the chain buffer is uint32[CW_CHAIN_MAX_POS + N] */
 #define CW_FRESH_WORDS 18 /* delta transport: uint32 words of a re-seeded world's sparse record (see cw_step_delta) */
 
 /* argument errors */
@@ -120,6 +121,23 @@ int cw_render(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, u
  * obs may be NULL (no pixels: step + auto-reset + the compact goal outputs of CwState only). */
 int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
                    uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, void* stream);
+
+/* cw_step_render for an OPEN-LOOP run of steps (action tape known in advance, e.g. a CUDA graph of K steps): the same
+ * launch per step, but consecutive launches are chained by per-group dataflow instead of whole-grid dependencies.
+ *   chain      device uint32[CW_CHAIN_MAX_POS + N], owned by the caller, used only by the chain
+ *   chain_pos  0 opens a chain: an ordinary launch (ordered after everything earlier in the stream) that also clears
+ *              `chain`.  chain_pos = i > 0: the caller guarantees that the operation immediately before it in `stream` is
+ *              the launch with chain_pos = i-1 of the same chain (same cfg / state / N / flags / stats / reward / done /
+ *              goal_obs / init_obs) and that `actions` (and every other input) was final before the chain opened.  Such a
+ *              launch does not wait for its predecessor GRID: the CTA that steps a group of worlds waits only for the
+ *              predecessor's state of that group, so composing step i overlaps the draining frame stores of step i-1.
+ *   obs_ring   the `obs` pointers of the chain rotate over this many distinct buffers (1 = the same buffer every step):
+ *              position i stores its first frame only after position i-obs_ring has completed.
+ * Grids still complete in stream order, so anything after the chain in the stream sees all of it.  Results are
+ * identical to the same sequence of cw_step_render calls. */
+int cw_step_render_chained(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
+                           uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, uint32_t* chain,
+                           int chain_pos, int obs_ring, void* stream);
 
 /* step + auto-reset WITHOUT device frames, for a host-side frame mirror ("delta transport"): instead of 48*H*W bytes of
  * pixels per world, each world gets one 16-byte record

@@ -328,6 +328,58 @@ def test_step_is_cuda_graph_capturable(cw):
         assert torch.equal(getattr(env, key), getattr(ref, key)), key
 
 
+@pytest.mark.parametrize("N,size,max_steps,ring,K,graph", [
+    (64, 7, 3, 1, 40, True),          # tiny launches: several chain positions co-resident, one frame buffer, resets every <= 3 steps
+    (300, 7, 2, 3, 48, True),         # a world can be re-seeded in consecutive positions (goal / init frames have no ring)
+    (4096, 21, 20, 4, 128, True),     # the bench shape: one CTA wave per launch
+    (5000, 21, 300, 2, 64, False),    # chained launches outside a graph
+    (40000, 21, 10, 2, 16, True),     # persistent launches (more groups than CTAs)
+    (700, 32, 6, 2, 24, True),        # multi-chunk frames
+])
+def test_chained_steps_match_unchained(cw, N, size, max_steps, ring, K, graph):
+    """cw_step_render_chained (per-group dataflow between consecutive launches) == the same steps launched one by one."""
+    acts = torch.from_numpy(np.random.RandomState(N + K).randint(0, 6, (K, N)).astype(np.uint8)).cuda()
+    kw = dict(size=(size, size), max_steps=max_steps, seed=21, obs_buffers=ring)
+    ref = cw.BatchedCraftingWorldEnv(N, **kw)
+    env = cw.BatchedCraftingWorldEnv(N, **kw)
+    ref.reset(); env.reset()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        env.step(acts[0]); env.step(acts[0], chain_pos=0)       # warm both launch paths outside the capture
+        ref.step(acts[0]); ref.step(acts[0])
+        s.synchronize()
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for k in range(K):
+                    env.step(acts[k], chain_pos=k)
+        for rep in range(3):                                      # every replay re-opens the chain at position 0
+            if graph:
+                g.replay()
+            else:
+                for k in range(K):
+                    env.step(acts[k], chain_pos=k)
+            for k in range(K):
+                ref.step(acts[k])
+            s.synchronize()
+            for key in ("grid", "init_grid", "agent", "goal", "t", "episode", "reward", "done", "desired_goal", "init_obs", "stats_raw"):
+                assert torch.equal(getattr(env, key), getattr(ref, key)), (key, rep)
+            for b in range(ring):
+                assert torch.equal(env._obs_ring[b], ref._obs_ring[b]), ("frame buffer", b, rep)
+
+
+def test_chained_step_rejects_bad_arguments(cw):
+    env = cw.BatchedCraftingWorldEnv(8, size=(5, 5), seed=1, obs_mode="compact")
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(8, dtype=torch.uint8, device="cuda"), chain_pos=0)
+    env = cw.BatchedCraftingWorldEnv(8, size=(5, 5), seed=1)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(8, dtype=torch.uint8, device="cuda"), chain_pos=1024)
+
+
 def test_host_env_matches_oracle(cw):
     """The host-buffer API (cw_host_*): NumPy in / NumPy out, sliced + pipelined inside the library."""
     N, seed, K = 3000, 55, 30
