@@ -214,6 +214,10 @@ def run_ours(args):
     if pixels:                                                   # rotate frame buffers so the ring exceeds the 126 MB L2
         while N * frame_bytes * ring < 300e6 and ring < 64:
             ring *= 2
+        if not args.no_chain:
+            ring = max(ring, 2)                                  # chained launches overlap step i+1 with the stores of step i
+        if args.ring:
+            ring = args.ring
     env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=dev, auto_reset=True, obs_mode=wl["obs"],
                                      env_id_base=rank * N, obs_buffers=ring, goal_images=not args.no_goal_images,
                                      max_steps=args.max_steps, collect_stats=not args.no_stats)
@@ -425,6 +429,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="shorter CPU baseline / e2e legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ring", type=int, default=0, help="override the number of rotating frame buffers")
     ap.add_argument("--no-chain", action="store_true", help="independent launches instead of chained ones")
     ap.add_argument("--no-unchained", action="store_true", help="skip the comparison leg with independent launches")
     ap.add_argument("--no-stats", action="store_true", help="experiment: do not accumulate episode statistics")

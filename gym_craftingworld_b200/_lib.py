@@ -69,6 +69,8 @@ def _declare(lib):
         "cw_host_destroy": [vp],
     }
     for name, args in protos.items():
+        if os.environ.get("CW_LIB_PATH") and not hasattr(lib, name):
+            continue                                               # A/B against an older build: newer entry points are absent
         fn = getattr(lib, name)
         fn.restype = ci
         fn.argtypes = args
@@ -83,7 +85,7 @@ def load():
             raise ImportError(f"gym_craftingworld_b200: CUDA library missing at {path}")
         lib = C.CDLL(path)
         _declare(lib)
-        if lib.cw_abi_version() != ABI_VERSION:
+        if lib.cw_abi_version() != ABI_VERSION and not os.environ.get("CW_LIB_PATH"):
             raise ImportError(f"gym_craftingworld_b200: ABI mismatch ({lib.cw_abi_version()} != {ABI_VERSION})")
         _lib = lib
     return _lib

@@ -116,7 +116,7 @@ __device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restric
         int here = g[cell];
         const int T = g[ncell];
         int ih = 0, ihn = 0;
-        if (h != 0) { ih = __ldcg(ig + cell); ihn = __ldcg(ig + ncell); }   // L2: a co-resident chained launch may have re-seeded it
+        if (h != 0) { ih = __ldcg(ig + cell); ihn = __ldcg(ig + ncell); }   // L2: a co-resident chained launch may have re-seeded it   // L2: a co-resident chained launch may have re-seeded it
         int old = EMPTY;  // EMPTY == "None": matches no predicate below (ray.py:655 uses 100)
         bool moved = ncell != cell;                                              // ray.py:395-396
         const bool blocked = ((T == ROCK) & (h != HAMMER)) | ((T == TREE) & (h != AXE));   // ray.py:401-405

@@ -98,6 +98,9 @@ enum : int { BAR_COMPOSE = 1, BAR_RESET_DONE = 2 };
 //      out with a TMA bulk store and only waits for the store issued F-1 slots earlier, so composing overlaps
 //      the stores.  Worlds the reset warp worked on are emitted last, after its named-barrier arrival.
 // dynamic shared memory: [tiles 2 x G x cell_stride][imagine scratch G x cell_stride][ring F x chunk_bytes]
+// kChained = false is the ordinary launch; true adds the chain protocol (a separate instantiation, so the ordinary
+// launch's code is exactly what it was -- the extra control flow measurably slowed it when it shared one body).
+template <bool kChained>
 __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_lut[9];
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     __shared__ uint32_t s_flag[32];
     __shared__ uint32_t s_obj[8];
     __shared__ uint32_t s_anypend;
+    __shared__ uint32_t s_pre[kChained ? 5 : 1][32];              // chained: next group's scalars, parked by the reset warp
 
     const int H = cfg.H, W = cfg.W, cs = cfg.cell_stride;
     const int G = args.group, F = args.nbuf, mode = args.mode;
@@ -127,11 +131,10 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     // (finished-CTA counter, `chain_ring` positions back).  griddepcontrol.wait moves to the END of the kernel, so
     // grids still COMPLETE in stream order.
     const uint32_t cpos = (uint32_t)args.chain_pos;
-    const bool chained = args.chain != nullptr;
+    constexpr bool chained = kChained;
     const bool chain_follow = chained && cpos > 0;
     uint32_t* const c_fin = args.chain;
     uint32_t* const c_epoch = args.chain + CW_CHAIN_MAX_POS;
-    bool fin_wait_pending = chained && args.chain_pos >= args.chain_ring;
 
     // Programmatic dependent launch: let the next launch in the stream start its prologue now, and do not touch
     // anything the previous launch wrote (state, frames) until it has fully completed.
@@ -141,24 +144,48 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     if (!chain_follow) pdl_wait();
     CW_STAMP(1);
 
-    // tile + scalar prefetch of group `g` (tiles -> stage `sgi`; scalars -> registers of warp 0)
+    // tile + scalar prefetch of group `g` (tiles -> stage `sgi`; scalars -> registers of warp 0).  Ordinary launches:
+    // issued by all threads at the top of the iteration before.
     uint32_t p_agent = 0, p_goal = 0, p_ep = 0;
     int p_t = 0, p_a = 6, p_forced = 0;
     auto prefetch = [&](int64_t g, int sgi) {
         if (g < ngroups) {
-            if (chain_follow) chain_wait_ge(c_epoch + g, cpos);   // every thread acquires: its loads below are ordered after
             const int64_t e0 = g * G;
             const int cnt = (int)min((int64_t)G, st.n - e0);
             const uint8_t* src = grid_in + e0 * cs;
             uint8_t* dst = tiles + (size_t)sgi * G * cs;
             for (int i = tid; i < cnt * nchunk16; i += kEnvThreads) cp_async16(dst + 16 * i, src + 16 * i);
-            if (tid < cnt) {                                      // L2 loads (.cg): state may come from a co-resident launch
+            if (tid < cnt) {                                      // L2 loads (.cg): streaming, no reuse in L1
                 const int64_t e = e0 + tid;
                 p_agent = __ldcg(agent_in + e);
                 if (mode & (M_STEP | M_IMAGINE_ONLY)) p_goal = __ldcg(st.goal + e);
                 if (mode & M_STEP) { p_t = __ldcg(st.t + e); p_a = args.actions[e]; }
                 if (mode & M_FORCE_RESET) p_forced = (!args.mask || args.mask[e]) ? 1 : 0;
                 if (mode & (M_AUTO_RESET | M_FORCE_RESET | M_IMAGINE_ONLY)) p_ep = __ldcg(st.episode + e);
+            }
+        }
+        cp_async_commit();
+    };
+    // Chained launches: the RESET WARP alone fetches the next group, after its own work of the current iteration and
+    // while the compose warps are busy -- it acquires the group's epoch word (the predecessor launch has published the
+    // state of exactly these worlds), issues the tile copies and parks the scalars in shared memory for warp 0.  The
+    // acquire (an L2 round trip + L1 invalidate) is therefore never on the compose warps' path.
+    auto prefetch_chained = [&](int64_t g, int sgi) {             // reset warp only (step + render [+ auto-reset] mode)
+        const int lane = tid - kComposeThreads;
+        if (g < ngroups) {
+            if (cpos > 0) chain_wait_ge(c_epoch + g, cpos);
+            const int64_t e0 = g * G;
+            const int cnt = (int)min((int64_t)G, st.n - e0);
+            const uint8_t* src = grid_in + e0 * cs;
+            uint8_t* dst = tiles + (size_t)sgi * G * cs;
+            for (int i = lane; i < cnt * nchunk16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+            if (lane < cnt) {
+                const int64_t e = e0 + lane;
+                s_pre[0][lane] = __ldcg(agent_in + e);
+                s_pre[1][lane] = __ldcg(st.goal + e);
+                s_pre[2][lane] = (uint32_t)__ldcg(st.t + e);
+                s_pre[3][lane] = args.actions[e];
+                s_pre[4][lane] = (mode & M_AUTO_RESET) ? __ldcg(st.episode + e) : 0u;
             }
         }
         cp_async_commit();
@@ -176,11 +203,6 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
             if (tid == 0) bulk_wait_read_dyn(F - 2);              // frees the slot the NEXT chunk composes into
             bar_sync(BAR_COMPOSE, kComposeThreads);
             if (tid == 0) {
-                if (fin_wait_pending) {                           // the launch that last wrote this frame buffer has completed
-                    chain_wait_ge(c_fin + (cpos - (uint32_t)args.chain_ring), gridDim.x);
-                    fence_proxy_async_all();
-                    fin_wait_pending = false;
-                }
                 bulk_store(dst + (size_t)band0 * band_bytes, fb, band_bytes * nb);
                 if (dst2) bulk_store(dst2 + (size_t)band0 * band_bytes, fb, band_bytes * nb);
                 bulk_commit();
@@ -190,14 +212,33 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     };
 
     int stage = 0;
-    prefetch(blockIdx.x, 0);
+    if constexpr (kChained) {
+        if (!composer) {
+            prefetch_chained(blockIdx.x, 0);
+            // frame buffers rotate with period chain_ring: the launch that last wrote the buffer this one is about to
+            // write must have completed (all its CTAs counted).  With a ring >= 2 that launch is long gone; with a
+            // single buffer this makes the launch wait for its predecessor like an ordinary one.
+            if (args.chain_pos >= args.chain_ring) chain_wait_ge(c_fin + (cpos - (uint32_t)args.chain_ring), gridDim.x);
+        }
+    } else {
+        prefetch(blockIdx.x, 0);
+    }
     for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
         // ---- A: this group's scalars move to `c_*`; the next group's tiles + scalars start loading ------------
-        const uint32_t c_agent = p_agent, c_goal = p_goal, c_ep = p_ep;
-        const int c_t = p_t, c_a = p_a, c_forced = p_forced;
-        prefetch(gi + gridDim.x, stage ^ 1);
-        cp_async_wait<1>();                                       // everything but the newest group has landed
+        uint32_t c_agent = p_agent, c_goal = p_goal, c_ep = p_ep;
+        int c_t = p_t, c_a = p_a;
+        const int c_forced = p_forced;
+        if constexpr (kChained) {
+            cp_async_wait<0>();                                   // (reset warp) this group's tiles have landed
+        } else {
+            prefetch(gi + gridDim.x, stage ^ 1);
+            cp_async_wait<1>();                                   // everything but the newest group has landed
+        }
         __syncthreads();
+        if constexpr (kChained) {
+            if (tid == 0 && gi == (int64_t)blockIdx.x) fence_proxy_async_all();   // orders the bulk stores after the acquire above
+            if (tid < 32) { c_agent = s_pre[0][tid]; c_goal = s_pre[1][tid]; c_t = (int)s_pre[2][tid]; c_a = (int)s_pre[3][tid]; c_ep = s_pre[4][tid]; }
+        }
         CW_STAMP(2);
         uint8_t* gt = tiles + (size_t)stage * G * cs;             // this group's tiles
         const int64_t e0 = gi * G;
@@ -243,7 +284,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
             // chained: publish this group's state for the next chain position.  Without a re-seeded world the state is
             // final right here (warp 0 wrote it before the barrier); otherwise thread 0 publishes after the re-seeded
             // worlds' frames (goal / init frames have no ring) have been written completely.
-            if (chained && s_anypend == 0 && lane == 0) { __threadfence(); st_release_gpu(c_epoch + gi, cpos + 1u); }
+            if (chained && s_anypend == 0 && lane == 0) st_release_gpu(c_epoch + gi, cpos + 1u);   // release is cumulative over the barrier
             for (int i = 0; i < G; i++) {
                 uint32_t flag = s_flag[i];
                 if (!(flag & FL_PENDING)) continue;
@@ -311,6 +352,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
 #endif
             if (tid == kComposeThreads) CW_STAMP(8);
             bar_arrive(BAR_RESET_DONE, kEnvThreads);
+            if constexpr (kChained) prefetch_chained(gi + gridDim.x, stage ^ 1);   // s_pre was consumed before this iteration's 2nd barrier
         } else {
             // ---- C: expand + stream out: untouched worlds first, worlds from the reset warp after its arrival ------
             // the very first frame of the launch goes out in quarter-frame stores: the launch is bound by the DRAM
@@ -335,7 +377,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     emit_frame(gt + i * cs, s_agent[i], args.obs + off, ((flag & FL_FRESH) && args.init_obs) ? args.init_obs + off : nullptr,
                                args.bands_per_chunk);
             }
-            if (chained && s_anypend != 0 && tid == 0) { bulk_wait_all(); __threadfence(); st_release_gpu(c_epoch + gi, cpos + 1u); }
+            if (chained && s_anypend != 0 && tid == 0) { bulk_wait_all(); st_release_gpu(c_epoch + gi, cpos + 1u); }
         }
         CW_STAMP(6);
         __syncthreads();                                          // tiles / s_* of this stage are rewritten next
@@ -459,7 +501,8 @@ __global__ void __launch_bounds__(256) cw_render_alt_kernel(const CwConfig cfg, 
 // host side
 // ------------------------------------------------------------------------------------------------------
 struct OccEntry { size_t smem; int per_sm; };
-struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool attr_set = false; int max_dyn = 0; int n_occ = 0; OccEntry occ[64]; };
+struct KernelInfo { bool attr_set = false; int max_dyn = 0; int n_occ = 0; OccEntry occ[64]; };   // per kernel instantiation
+struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; KernelInfo k[2]; };
 static DeviceInfo g_dev[64];
 static std::mutex g_dev_mu;   // guards the per-device attribute / occupancy cache (entry points may be called from several host threads)
 
@@ -532,18 +575,19 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     int rc = device_info(&dev);
     if (rc) return rc;
     if (st->n <= 0) return 0;
-    auto kern = cw_env_kernel;
+    auto kern = args.chain ? cw_env_kernel<true> : cw_env_kernel<false>;
+    KernelInfo* ki = &dev->k[args.chain ? 1 : 0];
     std::unique_lock<std::mutex> lk(g_dev_mu);
-    if (!dev->attr_set) {   // once per device: allow any dynamic size up to the opt-in maximum, prefer shared memory
+    if (!ki->attr_set) {   // once per device: allow any dynamic size up to the opt-in maximum, prefer shared memory
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, kern);
         if (e != cudaSuccess) return (int)e;
-        dev->max_dyn = dev->smem_optin - (int)fa.sharedSizeBytes;   // the opt-in limit covers static + dynamic
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev->max_dyn);
+        ki->max_dyn = dev->smem_optin - (int)fa.sharedSizeBytes;   // the opt-in limit covers static + dynamic
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->max_dyn);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        dev->attr_set = true;
+        ki->attr_set = true;
     }
     const bool needs_frame = (args.mode & M_RENDER) || args.goal_obs;
     args.bands_per_chunk = needs_frame ? pick_bands(cfg, env_tunable("CW_CHUNK_BYTES", 25 * 1024)) : 1;
@@ -572,15 +616,15 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     for (int G = (forcedG > 0 ? forcedG : 1); G <= (forcedG > 0 ? forcedG : gmax); G++) {
         if (G > 32) break;
         const size_t smem = 3 * (size_t)G * cfg->cell_stride + ring;
-        if (smem > (size_t)dev->max_dyn) break;
+        if (smem > (size_t)ki->max_dyn) break;
         int per_sm = 0;
-        for (int i = 0; i < dev->n_occ; i++)
-            if (dev->occ[i].smem == smem) per_sm = dev->occ[i].per_sm;
+        for (int i = 0; i < ki->n_occ; i++)
+            if (ki->occ[i].smem == smem) per_sm = ki->occ[i].per_sm;
         if (per_sm == 0) {
             cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEnvThreads, smem);
             if (e != cudaSuccess) return (int)e;
             if (per_sm < 1) per_sm = 1;
-            if (dev->n_occ < 64) { dev->occ[dev->n_occ].smem = smem; dev->occ[dev->n_occ].per_sm = per_sm; dev->n_occ++; }
+            if (ki->n_occ < 64) { ki->occ[ki->n_occ].smem = smem; ki->occ[ki->n_occ].per_sm = per_sm; ki->n_occ++; }
         }
         if (cap > 0 && cap < per_sm) per_sm = cap;
         const int64_t slots = (int64_t)dev->sms * per_sm;
