@@ -57,7 +57,7 @@ def _declare(lib):
         "cw_step_render": [cfgp, stp, vp, vp, vp, vp, vp, vp, vp, ci, vp],
         "cw_step_render_chained": [cfgp, stp, vp, vp, vp, vp, vp, vp, vp, ci, vp, ci, ci, vp],
         "cw_rollout": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
-        "cw_step_delta": [cfgp, stp, vp, vp, vp, vp, ci, vp],
+        "cw_step_delta": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
         "cw_imagine": [cfgp, stp, vp, vp],
         "cw_onehot": [cfgp, vp, vp, vp, i64, vp],
         "cw_render_alt": [cfgp, vp, vp, vp, i64, vp],

@@ -23,6 +23,13 @@
 
 // ---- a small persistent worker pool for the host-side frame patching of the delta transport -----------------
 namespace {
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
 class WorkerPool {
 public:
     explicit WorkerPool(int nthreads) : n_(nthreads < 1 ? 1 : nthreads) {
@@ -33,15 +40,16 @@ public:
         cv_.notify_all();
         for (auto& t : th_) t.join();
     }
-    // run job(tid, nthreads) on every thread (the caller is tid 0); returns when all are done
-    void run(const std::function<void(int, int)>& job) {
+    // start job(tid, nthreads) on the worker threads (tid 1..n-1); the caller then does whatever it wants (e.g. launch
+    // the kernel whose output the workers are already polling for), runs tid 0 itself and joins
+    void start(const std::function<void(int, int)>& job) {
         job_ = &job;
         remaining_.store(n_ - 1, std::memory_order_release);
         { std::lock_guard<std::mutex> lk(m_); gen_.fetch_add(1, std::memory_order_release); }
         cv_.notify_all();
-        job(0, n_);
-        while (remaining_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
     }
+    bool done() const { return remaining_.load(std::memory_order_acquire) == 0; }
+    int size() const { return n_; }
 private:
     void loop(int tid) {
         uint64_t seen = 0;
@@ -72,8 +80,23 @@ private:
 };
 
 // COLORS_N (ray.py:28-30)
-const uint8_t kLut[9][3] = {{0, 0, 0},   {110, 69, 39},  {255, 105, 180}, {100, 100, 200}, {100, 100, 100},
+constexpr uint8_t kLut[9][3] = {{0, 0, 0},   {110, 69, 39},  {255, 105, 180}, {100, 100, 200}, {100, 100, 100},
                             {0, 128, 0}, {205, 133, 63}, {197, 91, 97},   {240, 230, 140}};
+
+// the same colours repeated over 4 pixels (a full cell row) and over 2 pixels (an overlay row)
+struct LutRows {
+    uint8_t r12[9][12], r6[9][6];
+    constexpr LutRows() : r12(), r6() {
+        for (int c = 0; c < 9; c++) {
+            for (int k = 0; k < 12; k++) r12[c][k] = kLut[c][k % 3];
+            for (int k = 0; k < 6; k++) r6[c][k] = kLut[c][k % 3];
+        }
+    }
+};
+constexpr LutRows kRows;
+constexpr auto& kLut12 = kRows.r12;
+constexpr auto& kLut6 = kRows.r6;
+const uint8_t kWhite6[6] = {255, 255, 255, 255, 255, 255};
 
 // one cell of a host frame: 4x4 pixels of the object's colour, agent overlay on top (ray.py:550-557)
 inline void patch_cell(uint8_t* frame, int W, int cell, int code, bool agent_here, int hold) {
@@ -127,6 +150,9 @@ struct CwHostEnv {
     uint8_t* mirror_obs;              // caller buffers the mirror currently describes
     uint8_t* mirror_goal;
     WorkerPool* pool;
+    uint32_t seq;                     // sequence tag of the last delta step (1..63)
+    const uint8_t* pinned_actions;    // last caller action buffer found to be page-locked
+    bool nopatch;                     // CW_HOST_NOPATCH=1 (diagnostics only): consume the records, skip the frame patching
 };
 
 #define CW_HOST_MAGIC 0x43574845u
@@ -208,6 +234,8 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
             e->m_agent = (uint32_t*)malloc(n * 4);
             if (!e->m_grid || !e->m_agent) rc = (int)cudaErrorMemoryAllocation;
             e->pool = new (std::nothrow) WorkerPool(host_threads(n));
+            if (!rc && e->h_delta) memset(e->h_delta, 0, n * sizeof(uint4));   // tag 0 = never written
+            if (const char* np = getenv("CW_HOST_NOPATCH")) e->nopatch = *np == '1';
         }
     }
     TRY(cudaStreamCreateWithFlags(&e->streams[0], cudaStreamNonBlocking));
@@ -258,7 +286,10 @@ int cw_host_reset(CwHostEnv* e, uint8_t* obs_host, uint8_t* goal_obs_host) {
     return 0;
 }
 
-// delta transport: one launch writing 16-byte records into mapped pinned memory, then the pool patches the frames
+// delta transport: one launch writing 16-byte records into mapped pinned memory; the pool patches the frames WHILE the
+// kernel runs.  There is no stream synchronisation on this path: every record carries the step's 6-bit sequence tag
+// (one 16-byte store, preceded system-wide by the sparse record of a re-seeded world), the workers are started before
+// the launch and poll the records of their slice; when every record of the step has been consumed the step is complete.
 static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward_host, uint8_t* done_host, uint8_t* obs_host) {
     cudaStream_t s = e->streams[0];
     const int64_t n = e->st.n;
@@ -272,19 +303,35 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
         CK(cudaStreamSynchronize(s));
         e->mirror_obs = obs_host;
     }
-    int rc = cw_step_delta(&e->cfg, &e->st, act_src, e->h_delta, e->h_fresh, e->d_stats, e->flags & CW_F_AUTO_RESET, s);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(s));
+    e->seq = e->seq >= 63 ? 1 : e->seq + 1;                       // 1..63; 0 is the never-written state of the buffer
+    const uint32_t seq = e->seq;
     const size_t fb = e->frame_bytes;
     uint8_t* goal = e->mirror_goal;
-    const std::function<void(int, int)> job = [=](int tid, int nt) {
+    std::atomic<int> failed{0};
+    const bool nopatch = e->nopatch;
+    const std::function<void(int, int)> job = [&, n, H, W, cs, seq, fb, goal, nopatch](int tid, int nt) {
         const int64_t lo = n * tid / nt, hi = n * (tid + 1) / nt;
         uint8_t tmp[CW_MAX_SIDE * CW_MAX_SIDE];
+        const size_t rowb = (size_t)12 * W;
         for (int64_t w = lo; w < hi; w++) {
+            const volatile uint32_t* tag = &reinterpret_cast<const volatile uint32_t*>(e->h_delta + w)[2];
+            if ((*tag >> 26) != seq) {                            // not there yet: poll (the GPU's write invalidates the line)
+                uint64_t spins = 0;
+                while ((*tag >> 26) != seq) {
+                    if (failed.load(std::memory_order_relaxed)) return;
+                    if ((++spins & 0xFFFFF) == 0 && tid == 0 && cudaStreamQuery(s) != cudaErrorNotReady) {
+                        // the launch has finished (or failed): every record is in host memory now, or never will be
+                        if ((*tag >> 26) != seq) { failed.store(1); return; }
+                    }
+                    cpu_relax();
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
             const uint4 r = e->h_delta[w];
             const uint32_t flags = r.z >> 24;
             reward_host[w] = (int32_t)r.w;
             done_host[w] = (uint8_t)(flags & 1u);
+            if (nopatch) continue;
             uint8_t* g = e->m_grid + w * cs;
             uint8_t* frame = obs_host + w * fb;
             if (flags & 2u) {                                     // re-seeded: rebuild tile + frame (+ goal frame)
@@ -298,21 +345,52 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
                     for (int k = 8; k < 16; k++) if (fr[k] >> 16) tmp[fr[k] & 0xFFFFu] = (uint8_t)(fr[k] >> 16);
                     render_frame(goal + w * fb, H, W, tmp, fr[16]);
                 }
-            } else {                                              // patch the <= 3 cells that changed (render_edit)
-                const uint32_t old = e->m_agent[w];
-                const int wcell = (int)(r.z & 0xFFFFu);
-                if (wcell != 0xFFFF) g[wcell] = (uint8_t)((r.z >> 16) & 0xFFu);
-                if (wcell == 0xFFFF && old == r.x) continue;      // nothing visible changed
-                e->m_agent[w] = r.x;
-                const int oc = (int)(old & 0xFF) * W + (int)((old >> 8) & 0xFF);
-                const int nc = (int)(r.x & 0xFF) * W + (int)((r.x >> 8) & 0xFF), hold = (int)((r.x >> 16) & 0xFF);
-                if (oc != nc) patch_cell(frame, W, oc, g[oc], false, 0);
-                if (wcell != 0xFFFF && wcell != nc && wcell != oc) patch_cell(frame, W, wcell, g[wcell], false, 0);
-                patch_cell(frame, W, nc, g[nc], true, hold);
+                continue;
             }
+            // render_edit (ray.py:522-557) on the <= 2 cells a step can change.  A cell whose OBJECT is unchanged differs
+            // only in the centred 2x2 overlay block, so it costs two 6-byte writes instead of four 12-byte rows.
+            const uint32_t old = e->m_agent[w];
+            const int wcell = (int)(r.z & 0xFFFFu);
+            if (wcell != 0xFFFF) g[wcell] = (uint8_t)((r.z >> 16) & 0xFFu);
+            else if (old == r.x) continue;                        // nothing visible changed
+            e->m_agent[w] = r.x;
+            const int orow = (int)(old & 0xFF), ocol = (int)((old >> 8) & 0xFF);
+            const int nrow = (int)(r.x & 0xFF), ncol = (int)((r.x >> 8) & 0xFF), hold = (int)((r.x >> 16) & 0xFF);
+            const int oc = orow * W + ocol, nc = nrow * W + ncol;
+            uint8_t* po = frame + (size_t)(4 * orow) * rowb + 12 * ocol;
+            uint8_t* pn = frame + (size_t)(4 * nrow) * rowb + 12 * ncol;
+            if (oc != nc) {                                       // the agent left `oc`; its object did not change
+                const uint8_t* col = kLut6[g[oc]];
+                memcpy(po + rowb + 3, col, 6); memcpy(po + 2 * rowb + 3, col, 6);
+            }
+            if (wcell != 0xFFFF && wcell != nc) patch_cell(frame, W, wcell, g[wcell], false, 0);   // (not produced by step())
+            if (wcell == nc) {                                    // the object under the agent changed: all four rows
+                const uint8_t* col = kLut12[g[nc]];
+                for (int y = 0; y < 4; y++) memcpy(pn + y * rowb, col, 12);
+            }
+            memset(pn + rowb + 3, 255, 6);                        // ray.py:555
+            memcpy(pn + 2 * rowb + 3, hold ? kLut6[hold] : kWhite6, 6);   // ray.py:556-557
         }
     };
-    e->pool->run(job);
+    e->pool->start(job);                                          // workers poll while the launch is on its way
+    int rc = cw_step_delta(&e->cfg, &e->st, act_src, e->h_delta, e->h_fresh, e->d_stats, e->flags & CW_F_AUTO_RESET, (int)seq, s);
+    if (rc) failed.store(1);
+    job(0, e->pool->size());
+    // watchdog: once the launch has left the stream every record is in host memory; workers still polling 100 ms later
+    // will never be served (a failed launch) -- release them instead of hanging the caller
+    for (uint64_t k = 1; !e->pool->done(); k++) {
+        if ((k & 0x3FFF) == 0 && !rc && cudaStreamQuery(s) != cudaErrorNotReady) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while (!e->pool->done() && std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(100)) cpu_relax();
+            if (!e->pool->done()) failed.store(1);
+        }
+        cpu_relax();
+    }
+    if (rc) return rc;
+    if (failed.load()) {
+        cudaError_t ce = cudaStreamSynchronize(s);
+        return (int)(ce != cudaSuccess ? ce : cudaErrorUnknown);
+    }
     return 0;
 }
 
@@ -322,7 +400,10 @@ int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host
     CK(cudaSetDevice(e->device));
     const int64_t n = e->st.n;
     const uint8_t* act_src = actions_host;
-    if (!is_pinned(actions_host)) { memcpy(e->h_actions, actions_host, n); act_src = e->h_actions; }
+    if (actions_host != e->pinned_actions) {                     // the attribute query costs ~1 us: remember a pinned buffer
+        if (is_pinned(actions_host)) e->pinned_actions = actions_host;
+        else { memcpy(e->h_actions, actions_host, n); act_src = e->h_actions; }
+    }
     if (obs_host && (e->flags & CW_F_DELTA_TRANSPORT)) return host_step_delta(e, act_src, reward_host, done_host, obs_host);
     const bool direct = obs_host && is_pinned(obs_host);
     uint8_t* frames_dst = obs_host;
@@ -385,6 +466,8 @@ int cw_host_device_state(CwHostEnv* e, CwState* out_state, uint8_t** out_obs) {
 int cw_host_destroy(CwHostEnv* e) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     cudaSetDevice(e->device);
+    if (e->streams[0]) cudaStreamSynchronize(e->streams[0]);     // the delta path returns without a stream sync
+    if (e->streams[1]) cudaStreamSynchronize(e->streams[1]);
     cudaFree(e->st.grid); cudaFree(e->st.init_grid); cudaFree(e->st.agent); cudaFree(e->st.goal); cudaFree(e->st.t);
     cudaFree(e->st.episode); cudaFree(e->d_actions); cudaFree(e->d_reward); cudaFree(e->d_obs);
     cudaFree(e->d_goal_obs); cudaFree(e->d_stats);

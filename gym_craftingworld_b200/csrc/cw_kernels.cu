@@ -34,6 +34,7 @@ struct EnvArgs {
     unsigned long long* stats;
     uint4* delta;            // delta transport: per-world record {agent, goal, wcell | wval<<16 | flags<<24, reward} (nullable)
     uint32_t* fresh;         // delta transport: [N][CW_FRESH_WORDS] sparse record of a re-seeded world + its imagined goal
+    uint32_t delta_seq;      // delta transport: 6-bit sequence tag stored in bits 2..7 of the record's flag byte
     const uint8_t* rgrid;    // render-only entry: grid / agent given directly (state may be partial)
     const uint32_t* ragent;
     int mode;
@@ -266,8 +267,8 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     } else {
                         st.agent[e] = agent; st.goal[e] = goal; st.t[e] = t;
                         if (args.delta)                           // one 16-byte store (possibly into mapped host memory)
-                            args.delta[e] = make_uint4(agent, goal, (uint32_t)(wcell & 0xFFFF) | ((uint32_t)wval << 16) | ((dn ? 1u : 0u) << 24),
-                                                       (uint32_t)rew);
+                            args.delta[e] = make_uint4(agent, goal, (uint32_t)(wcell & 0xFFFF) | ((uint32_t)wval << 16) |
+                                                       (((dn ? 1u : 0u) | (args.delta_seq << 2)) << 24), (uint32_t)rew);
                     }
                     rew_stash = (uint32_t)rew;
                 }
@@ -304,8 +305,6 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
 #pragma unroll
                         for (int k = 0; k < 8; k++) word = lane == k ? (objs.cell[k] | (objs.code[k] << 16)) : word;
                         if (lane < 8) fr[lane] = word;
-                        if (lane == 0)
-                            args.delta[er] = make_uint4(ag, gl, 0xFFFFu | (3u << 24) /* done | fresh */, s_rew[i]);
                     }
                     if (args.goal_obs || st.goal_grid || args.delta) {   // desired_goal = imagine_obs(): ray.py:191, 220-299
                         uint32_t gag = ag;
@@ -317,6 +316,12 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                             for (int k = 0; k < 8; k++) word = lane == k ? (objs.cell[k] | (objs.code[k] << 16)) : word;
                             if (lane < 8) fr[8 + lane] = word;
                             if (lane == 8) fr[16] = gag;
+                            // the 16-byte record goes LAST: a consumer polling its sequence tag (possibly the host, through
+                            // mapped memory) must find the sparse record complete
+                            __threadfence_system();
+                            __syncwarp();
+                            if (lane == 0)
+                                args.delta[er] = make_uint4(ag, gl, 0xFFFFu | ((3u /* done | fresh */ | (args.delta_seq << 2)) << 24), s_rew[i]);
                         }
                         tile_from_objects(objs, nchunk16, simag + i * cs);
                         if (st.goal_grid) {                       // compact goal state (one-hot observation family)
@@ -554,14 +559,25 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);
 }
 
-static int env_tunable(const char* name, int dflt) {
+static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
+}
+// experiment knobs (tools/sweep*.sh), read from the environment ONCE: a host-buffer step is tens of microseconds and six
+// getenv scans per launch were a measurable part of it
+struct Tunables {
+    int bands_per_chunk = env_int("CW_BANDS_PER_CHUNK", 0), chunk_bytes = env_int("CW_CHUNK_BYTES", 25 * 1024);
+    int frame_buffers = env_int("CW_FRAME_BUFFERS", 0), first_split = env_int("CW_FIRST_SPLIT", 4);
+    int ctas_per_sm = env_int("CW_CTAS_PER_SM", 0), group = env_int("CW_GROUP", 0);
+};
+static const Tunables& tunables() {
+    static const Tunables t;
+    return t;
 }
 
 // frame chunking: the largest number of bands whose chunk fits the per-buffer budget
 static int pick_bands(const CwConfig* cfg, int budget_bytes) {
-    int forced = env_tunable("CW_BANDS_PER_CHUNK", 0);
+    int forced = tunables().bands_per_chunk;
     if (forced > 0) return forced < cfg->H ? forced : cfg->H;
     int bands = budget_bytes / (48 * cfg->W);
     if (bands < 1) bands = 1;
@@ -590,12 +606,12 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
         ki->attr_set = true;
     }
     const bool needs_frame = (args.mode & M_RENDER) || args.goal_obs;
-    args.bands_per_chunk = needs_frame ? pick_bands(cfg, env_tunable("CW_CHUNK_BYTES", 25 * 1024)) : 1;
+    args.bands_per_chunk = needs_frame ? pick_bands(cfg, tunables().chunk_bytes) : 1;
     // Ring depth F.  A launch of one or a few CTA waves (small batches) is fastest with F = 2 and 4 CTAs/SM; a persistent
     // launch over many groups wants a deeper ring and larger groups (fewer CTAs/SM, the per-group step phase amortised
     // over more worlds): measured on B200 at 21x21 (tools/sweep3.sh) F = 3 wins around 0.7 GB of frames per launch and
     // F = 4 from ~1.3 GB up (0.90 -> 0.95 of the HBM roofline at 131072 worlds).  Multi-chunk frames keep F = 2.
-    int F = env_tunable("CW_FRAME_BUFFERS", 0);
+    int F = tunables().frame_buffers;
     if (F <= 0) {
         const double frame_total = (double)st->n * 48.0 * cfg->H * cfg->W;
         const bool single_chunk = args.bands_per_chunk >= cfg->H;
@@ -604,14 +620,14 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     F = F < 2 ? 2 : (F > 6 ? 6 : F);
     args.nbuf = F;
     args.w_magic = (uint32_t)(0x100000000ull / (uint64_t)cfg->W) + 1u;
-    args.first_split = env_tunable("CW_FIRST_SPLIT", 4);
+    args.first_split = tunables().first_split;
     if (args.first_split < 1) args.first_split = 1;
     const size_t ring = needs_frame ? (size_t)F * 48 * cfg->W * args.bands_per_chunk : 0;
-    const int cap = env_tunable("CW_CTAS_PER_SM", 0);
+    const int cap = tunables().ctas_per_sm;
     // group size G: the per-SM critical path is (CTA waves) x G worlds; pick the G that minimises it
     int bestG = 0, best_per_sm = 1;
     int64_t best_cost = 0;
-    const int forcedG = env_tunable("CW_GROUP", 0);
+    const int forcedG = tunables().group;
     const int gmax = 16384 / cfg->cell_stride < 1 ? 1 : (16384 / cfg->cell_stride > 16 ? 16 : 16384 / cfg->cell_stride);
     for (int G = (forcedG > 0 ? forcedG : 1); G <= (forcedG > 0 ? forcedG : gmax); G++) {
         if (G > 32) break;
@@ -760,14 +776,16 @@ int cw_step_render_chained(const CwConfig* cfg, const CwState* st, const uint8_t
 }
 
 int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions, void* delta, uint32_t* fresh, int64_t* stats,
-                  int flags, void* stream) {
+                  int flags, int seq, void* stream) {
     int rc = check_config(cfg); if (rc) return rc;
     rc = check_state(st); if (rc) return rc;
     if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
     if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
     if (st->n == 0) return 0;
     if (!actions || !delta || !fresh) return CW_E_NULLPTR;
+    if (seq < 0 || seq > 63) return CW_E_BADCONFIG;
     EnvArgs a = {};
+    a.delta_seq = (uint32_t)seq;
     a.actions = actions; a.delta = (uint4*)delta; a.fresh = fresh; a.stats = (unsigned long long*)stats;
     a.reward = nullptr; a.done = nullptr;
     a.mode = M_STEP | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);

@@ -50,6 +50,11 @@ class HostCraftingWorldEnv:
         self.reward, self._rew_t = pinned_empty((N,), torch.int32)
         self._done_u8, self._done_t = pinned_empty((N,), torch.uint8)
         self._actions, self._act_t = pinned_empty((N,), torch.uint8)
+        # a step is tens of microseconds: resolve the buffer addresses and build the (in-place mutated) outputs once
+        self._step_args = (self._h, self._p(self._actions), self._p(self.reward), self._p(self._done_u8), self._p(self.obs))
+        self._done = self._done_u8.view(np.bool_)
+        self._obs_dict = {"observation": self.obs, "desired_goal": self.desired_goal, "achieved_goal": self.obs}
+        self._info = {}
 
     @property
     def h2d_bytes_per_step(self) -> int:
@@ -66,14 +71,16 @@ class HostCraftingWorldEnv:
 
     def reset(self):
         _lib.check(self._lib.cw_host_reset(self._h, self._p(self.obs), self._p(self.desired_goal)), "cw_host_reset")
-        return {"observation": self.obs, "desired_goal": self.desired_goal, "achieved_goal": self.obs}
+        return self._obs_dict
 
     def step(self, actions):
+        """``(obs dict, reward int32[N], done bool[N], info)``; like the reference (``ray.py:194-196, 359-360``) the returned
+        arrays are owned by the env and mutated in place by the next call."""
         np.copyto(self._actions, np.asarray(actions).reshape(-1), casting="unsafe")
-        _lib.check(self._lib.cw_host_step(self._h, self._p(self._actions), self._p(self.reward), self._p(self._done_u8),
-                                          self._p(self.obs)), "cw_host_step")
-        return ({"observation": self.obs, "desired_goal": self.desired_goal, "achieved_goal": self.obs}, self.reward,
-                self._done_u8.view(np.bool_), {})
+        rc = self._lib.cw_host_step(*self._step_args)
+        if rc:
+            _lib.check(rc, "cw_host_step")
+        return self._obs_dict, self.reward, self._done, self._info
 
     def stats(self):
         s = np.zeros(_lib.STATS_LEN, np.int64)

@@ -140,15 +140,17 @@ int cw_step_render_chained(const CwConfig* cfg, const CwState* st, const uint8_t
                            int chain_pos, int obs_ring, void* stream);
 
 /* step + auto-reset WITHOUT device frames, for a host-side frame mirror ("delta transport"): instead of 48*H*W bytes of
- * pixels per world, each world gets one 16-byte record
- *     delta[n] = { agent, goal, wcell | wval<<16 | flags<<24, reward }      flags: 1 done, 2 fresh (re-seeded)
- * (wcell = 0xFFFF: no grid cell written this step), and a world re-seeded in this call additionally gets
+ * pixels per world, each world gets one 16-byte record, written with ONE 16-byte store
+ *     delta[n] = { agent, goal, wcell | wval<<16 | flags<<24, reward }      flags: 1 done, 2 fresh (re-seeded),
+ *                                                                            bits 2..7 = `seq` (0..63), the caller's tag
+ * (wcell = 0xFFFF: no grid cell written this step), and a world re-seeded in this call additionally gets (written and
+ * fenced system-wide BEFORE its delta record, so a consumer that polls the tag finds them complete)
  *     fresh[n][0..7]  = cell | code<<16 of its 8 objects        fresh[n][8..15] = same for the imagined goal state
  *     fresh[n][16]    = agent word of the imagined goal state
  * `delta` / `fresh` may point into mapped pinned HOST memory (zero-copy): the consumer patches the <= 3 cells that changed
  * in its own copy of the frame (what the reference's render_edit does, ray.py:522-557). */
 int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions, void* delta /* uint4[N] */,
-                  uint32_t* fresh /* [N][CW_FRESH_WORDS] */, int64_t* stats, int flags, void* stream);
+                  uint32_t* fresh /* [N][CW_FRESH_WORDS] */, int64_t* stats, int flags, int seq, void* stream);
 
 /* K consecutive steps in one launch (open-loop action tape actions[K][N]); reward/done [K][N] nullable.
  * Same per-step semantics as cw_step. */
