@@ -362,7 +362,11 @@ def run_ours(args):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "algorithmic_bytes_per_env_step": B, "units_per_launch": N, "launch_us": launch_s * 1e6,
                          "peak_source": peak_src,
-                         "note": "launch duration = CUDA-event time of the timed region / launches (includes inter-kernel gaps)"},
+                         "note": "launch duration = CUDA-event time of the timed region / launches (includes inter-kernel gaps). "
+                                 "peak is the measured COPY bandwidth (read+write mix); this kernel is a ~98% write stream, which does "
+                                 "not pay a copy's read/write turnarounds, so frac can slightly exceed 1. traffic (ncu, one isolated "
+                                 "launch) is below the algorithmic bytes at 4096 worlds because the 126 MB L2 writes part of the frame "
+                                 "back after the profiled launch"},
             "cpu_baseline": cpu_base,
             "episode_stats_rank0": {k: stats_local[k] for k in ("episodes", "successes", "mean_return", "mean_length")},
         }
