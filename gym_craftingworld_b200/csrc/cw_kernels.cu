@@ -446,60 +446,182 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
     CW_WSTAMP(4);
 }
 
-// observation_vector (ray.py:94-98, 605-613): one 32-bit word (4 of the 12 channel bytes of a cell) per thread
-__global__ void __launch_bounds__(256) cw_onehot_kernel(const CwConfig cfg, const uint8_t* __restrict__ grid,
-                                                        const uint32_t* __restrict__ agent, uint32_t* __restrict__ out,
-                                                        int64_t n_words) {
-    const int HW = cfg.H * cfg.W;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t cellg = w / 3;
-        const int j = (int)(w - cellg * 3);
-        const int64_t env = cellg / HW;
-        const int cell = (int)(cellg - env * HW);
-        const int code = grid[env * cfg.cell_stride + cell];
-        const uint32_t ag = agent[env];
-        const int acell = (int)(ag & 0xFF) * cfg.W + (int)((ag >> 8) & 0xFF);
-        uint32_t v = 0;
-        const int ch = code - 1;                                  // object channel 0..7 (or -1)
-        if (ch >= 0 && (ch >> 2) == j) v |= 1u << (8 * (ch & 3));
-        if (cell == acell && j == 2) {
-            v |= 1u;                                              // channel 8: agent
-            const int h = (ag >> 16) & 0xFF;
-            if (h) v |= 1u << (8 * h);                            // channels 9..11: holding
-        }
-        out[w] = v;
+// ---- observation-format expanders (one-hot state, AltObs frames): staged in shared memory, streamed out by TMA ------
+// Both outputs are contiguous over (world, ...), so a work item is a contiguous BYTE RANGE of the output: it is composed
+// in shared memory at the same address phase (mod 16) as its destination; the 16-byte aligned body leaves with ONE TMA
+// bulk store (no LSU store instructions), the few head / tail bytes of a range that does not start / end on a 16-byte
+// boundary with element-sized stores.  Two stages: composing item i+1 overlaps the store of item i.  The global write
+// stream is therefore full-line whatever H, W and the world count are.
+constexpr int kExpThreads = 256;
+constexpr int kOneHotIters = 7;
+constexpr uint32_t kOneHotCells = kOneHotIters * kExpThreads;    // cells per work item (21 KB of output)
+constexpr uint32_t kOneHotStage = kOneHotCells * 12 + 32;
+constexpr uint32_t kAltBudget = 32 * 1024;       // bytes of AltObs output per work item
+constexpr uint32_t kAltStage = kAltBudget + 48;
+constexpr int kAltIters = 3;                     // cells per item <= kAltBudget / 54 = 606 <= 3 x 256
+
+template <int kGran>   // element size of head / tail copies: 2 or 4 bytes (s and g have the same address modulo 16)
+__device__ __forceinline__ void stream_out_same_phase(const uint8_t* s, uint8_t* g, uint32_t nbytes, int tid) {
+    const uint32_t head = min((16u - (uint32_t)((uintptr_t)g & 15u)) & 15u, nbytes);
+    const uint32_t body = (nbytes - head) & ~15u;
+    for (uint32_t i = tid * kGran; i < head; i += kExpThreads * kGran)
+        for (int q = 0; q < kGran; q++) g[i + q] = s[i + q];
+    for (uint32_t i = head + body + tid * kGran; i < nbytes; i += kExpThreads * kGran)
+        for (int q = 0; q < kGran; q++) g[i + q] = s[i + q];
+    if (tid == 0) {
+        if (body) bulk_store(g + head, s + head, body);
+        bulk_commit();                                            // (an empty group keeps the stage accounting uniform)
     }
 }
 
-// AltObs renderer (craftingworld_altobs.py:489-548): one thread per output pixel (3 x int16)
+// observation_vector (ray.py:94-98, 605-613): uint8[N][H][W][12].  A work item is kOneHotCells consecutive cells of the
+// flattened (world, cell) index; a thread builds the three 32-bit words of a cell's 12 channel bytes in registers.
+__global__ void __launch_bounds__(kExpThreads) cw_onehot_kernel(const CwConfig cfg, const uint8_t* __restrict__ grid,
+                                                                const uint32_t* __restrict__ agent, uint8_t* __restrict__ out,
+                                                                int64_t n_cells, uint32_t hw_magic) {
+    extern __shared__ __align__(16) uint8_t xsm[];
+    const uint32_t HW = (uint32_t)(cfg.H * cfg.W);
+    const int tid = threadIdx.x;
+    const int64_t items = (n_cells + kOneHotCells - 1) / kOneHotCells;
+    int stage = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, stage ^= 1) {
+        const int64_t c0 = it * kOneHotCells;
+        const uint32_t cnt = (uint32_t)min((int64_t)kOneHotCells, n_cells - c0);
+        const int64_t env0 = c0 / HW;
+        const uint32_t rem0 = (uint32_t)(c0 - env0 * HW);
+        uint8_t* dst = out + c0 * 12;
+        uint8_t* buf = xsm + stage * kOneHotStage + ((uintptr_t)dst & 15u);   // 4-byte aligned: c0 * 12 and the base pointer are
+        uint32_t code[kOneHotIters], ag[kOneHotIters], cell[kOneHotIters];
+#pragma unroll
+        for (int u = 0; u < kOneHotIters; u++) {                  // all loads of the item in flight together
+            const uint32_t j = tid + u * kExpThreads;
+            const uint32_t idx = rem0 + (j < cnt ? j : 0u);
+            const uint32_t de = __umulhi(idx, hw_magic);          // idx / HW  (idx < kOneHotCells + HW)
+            const int64_t env = env0 + de;
+            cell[u] = idx - de * HW;
+            code[u] = grid[env * cfg.cell_stride + cell[u]];
+            ag[u] = agent[env];
+        }
+        if (tid == 0) bulk_wait_read<1>();                        // the store that last read this stage has drained
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kOneHotIters; u++) {
+            const uint32_t j = tid + u * kExpThreads;
+            if (j >= cnt) continue;
+            const uint32_t acell = (ag[u] & 0xFF) * (uint32_t)cfg.W + ((ag[u] >> 8) & 0xFF);
+            uint32_t w0 = 0, w1 = 0, w2 = 0;
+            if (code[u] >= 1 && code[u] <= 4) w0 = 1u << (8 * (code[u] - 1));        // object channels 0..3
+            else if (code[u] >= 5 && code[u] <= 8) w1 = 1u << (8 * (code[u] - 5));   // object channels 4..7
+            if (cell[u] == acell) {
+                w2 = 1u;                                                             // channel 8: agent
+                const uint32_t h = (ag[u] >> 16) & 0xFF;
+                if (h >= 1 && h <= 3) w2 |= 1u << (8 * h);                           // channels 9..11: holding
+            }
+            uint32_t* p = reinterpret_cast<uint32_t*>(buf) + 3 * j;
+            p[0] = w0; p[1] = w1; p[2] = w2;
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        stream_out_same_phase<4>(buf, dst, cnt * 12, tid);
+    }
+    if (tid == 0) bulk_wait_all();
+}
+// fallback for an output pointer that is not 4-byte aligned: one byte-wise cell per thread
+__global__ void __launch_bounds__(256) cw_onehot_unaligned_kernel(const CwConfig cfg, const uint8_t* __restrict__ grid,
+                                                                  const uint32_t* __restrict__ agent, uint8_t* __restrict__ out,
+                                                                  int64_t n_cells) {
+    const int HW = cfg.H * cfg.W;
+    for (int64_t fc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; fc < n_cells; fc += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t env = fc / HW;
+        const int cell = (int)(fc - env * HW);
+        const int code = grid[env * cfg.cell_stride + cell];
+        const uint32_t ag = agent[env];
+        const int acell = (int)(ag & 0xFF) * cfg.W + (int)((ag >> 8) & 0xFF), h = (ag >> 16) & 0xFF;
+        uint8_t* o = out + fc * 12;
+        for (int ch = 0; ch < 12; ch++)
+            o[ch] = (uint8_t)((ch < 8 && code == ch + 1) || (cell == acell && (ch == 8 || (h >= 1 && h <= 3 && ch == 8 + h))));
+    }
+}
+
+// AltObs renderer (craftingworld_altobs.py:489-548): int16[N][3H+3][3W][3].  Sub-pixel k of a cell is lit with
+// CPV_COLORS[k] x the multiplicity of channel k, so a frame is almost all zeros: a work item (several whole worlds, or a
+// band of cell rows of one large world) is zero-filled in shared memory with 16-byte stores, the <= 3 lit sub-pixels of
+// each cell are scattered into it, and the range is streamed out.
 __device__ __constant__ int16_t kCPV[9][3] = {{45, 82, 160},  {255, 102, 102}, {204, 204, 0},   {211, 211, 211}, {34, 133, 34},
                                               {0, 215, 255},  {153, 52, 255},  {10, 215, 100},  {0, 0, 255}};   // altobs.py:26-27
-__global__ void __launch_bounds__(256) cw_render_alt_kernel(const CwConfig cfg, const uint8_t* __restrict__ grid,
-                                                            const uint32_t* __restrict__ agent, int16_t* __restrict__ out,
-                                                            int64_t n_pixels) {
-    const int H = cfg.H, W = cfg.W, PW = 3 * W, P = (3 * H + 3) * PW;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_pixels; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t env = idx / P;
-        const int p = (int)(idx - env * P);
-        const int y = p / PW, x = p - y * PW;
-        const uint32_t ag = agent[env];
-        const int ar = ag & 0xFF, ac = (ag >> 8) & 0xFF, h = (ag >> 16) & 0xFF;
-        int16_t v0 = 0, v1 = 0, v2 = 0;
-        if (y >= 3 * H) {                                          // status strip, altobs.py:542-545
-            if (h != 0 && x >= 3 && x < 6) { v0 = 255; v1 = 255; v2 = 255; }
-        } else {
-            const int r = y / 3, c = x / 3, k = (y - 3 * r) * 3 + (x - 3 * c);      // sub-pixel k of cell (r,c), altobs.py:45-51
-            const int code = grid[env * cfg.cell_stride + r * W + c];
-            int m = (k < 8 && code == k + 1) ? 1 : 0;              // object channels
-            if (r == ar && c == ac) {
-                if (k == 8) m = 1;                                 // agent channel
-                if (h != 0 && k == h - 1) m += 1;                  // held item added onto channels 0..2, altobs.py:531-533
-            }
-            v0 = (int16_t)(m * kCPV[k][0]); v1 = (int16_t)(m * kCPV[k][1]); v2 = (int16_t)(m * kCPV[k][2]);
+struct AltPlan { int worlds_per_item, bands, rows_per_band; int64_t items; uint32_t w_magic, cells_magic; };
+__global__ void __launch_bounds__(kExpThreads) cw_render_alt_kernel(const CwConfig cfg, const uint8_t* __restrict__ grid,
+                                                                    const uint32_t* __restrict__ agent, int16_t* __restrict__ out,
+                                                                    int64_t n, const AltPlan plan) {
+    extern __shared__ __align__(16) uint8_t xsm[];
+    const int H = cfg.H, W = cfg.W, PW = 3 * W;
+    const uint32_t P = (uint32_t)(3 * H + 3) * PW;                // pixels per frame
+    const int tid = threadIdx.x;
+    int stage = 0;
+    for (int64_t it = blockIdx.x; it < plan.items; it += gridDim.x, stage ^= 1) {
+        int64_t e0;
+        int nw, r0, r1;
+        bool last;
+        if (plan.bands == 1) { e0 = it * plan.worlds_per_item; nw = (int)min((int64_t)plan.worlds_per_item, n - e0); r0 = 0; r1 = H; last = true; }
+        else {
+            e0 = it / plan.bands; nw = 1;
+            const int b = (int)(it - e0 * plan.bands);
+            r0 = b * plan.rows_per_band; r1 = min(H, r0 + plan.rows_per_band); last = b == plan.bands - 1;
         }
-        int16_t* o = out + idx * 3;
-        o[0] = v0; o[1] = v1; o[2] = v2;
+        const uint32_t rows = (uint32_t)(r1 - r0);
+        const uint32_t item_pixels = nw > 1 ? (uint32_t)nw * P : (3u * rows + (last ? 3u : 0u)) * PW;
+        const uint32_t nbytes = item_pixels * 6;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(out) + ((size_t)e0 * P + (size_t)(3 * r0) * PW) * 6;
+        uint8_t* sbase = xsm + stage * kAltStage;
+        uint8_t* buf = sbase + ((uintptr_t)dst & 15u);            // even: int16 output
+        const uint32_t band_cells = rows * (uint32_t)W, ncell = (uint32_t)nw * band_cells;
+        uint32_t code[kAltIters], ag[kAltIters], wi[kAltIters], lr[kAltIters], cc[kAltIters];
+#pragma unroll
+        for (int u = 0; u < kAltIters; u++) {                     // all loads of the item in flight together
+            const uint32_t j = tid + u * kExpThreads, jj = j < ncell ? j : 0u;
+            wi[u] = __umulhi(jj, plan.cells_magic);               // j / band_cells
+            const uint32_t lc = jj - wi[u] * band_cells;          // cell within the band
+            lr[u] = __umulhi(lc, plan.w_magic);                   // row within the band
+            cc[u] = lc - lr[u] * (uint32_t)W;
+            const int64_t env = e0 + wi[u];
+            code[u] = grid[env * cfg.cell_stride + (uint32_t)(r0 + lr[u]) * (uint32_t)W + cc[u]];
+            ag[u] = agent[env];
+        }
+        if (tid == 0) bulk_wait_read<1>();                        // the store that last read this stage has drained
+        __syncthreads();
+        for (uint32_t i = tid; i < ((nbytes + 30u) >> 4); i += kExpThreads) reinterpret_cast<uint4*>(sbase)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        int16_t* px = reinterpret_cast<int16_t*>(buf);
+#pragma unroll
+        for (int u = 0; u < kAltIters; u++) {
+            if (tid + u * kExpThreads >= ncell) continue;
+            const uint32_t cell = (uint32_t)(r0 + lr[u]) * (uint32_t)W + cc[u];
+            const bool here = cell == (ag[u] & 0xFF) * (uint32_t)W + ((ag[u] >> 8) & 0xFF);
+            const uint32_t h = here ? ((ag[u] >> 16) & 0xFF) : 0u, cd = code[u];
+            int16_t* cellp = px + ((size_t)wi[u] * P + (size_t)(3 * lr[u]) * PW + 3 * cc[u]) * 3;
+            auto light = [&](uint32_t k, int mult) {              // sub-pixel k = (k / 3, k % 3) of the cell, altobs.py:45-51
+                int16_t* q = cellp + ((k / 3) * PW + (k % 3)) * 3;
+                q[0] = (int16_t)(mult * kCPV[k][0]); q[1] = (int16_t)(mult * kCPV[k][1]); q[2] = (int16_t)(mult * kCPV[k][2]);
+            };
+            const bool held = h >= 1 && h <= 3;                   // a held item adds onto channels 0..2, altobs.py:531-533
+            if (cd >= 1 && cd <= 8) light(cd - 1, 1 + ((held && h == cd) ? 1 : 0));
+            if (here) {
+                light(8, 1);                                      // agent channel
+                if (held && h != cd) light(h - 1, 1);
+            }
+        }
+        if (last) {                                               // status strip, altobs.py:542-545: columns 3..5 white while holding
+            for (uint32_t j = tid; j < (uint32_t)nw * 27u; j += kExpThreads) {
+                const uint32_t w = j / 27u, q = j - w * 27u, y = q / 9u, xq = q - y * 9u;
+                if (((agent[e0 + w] >> 16) & 0xFF) != 0)
+                    px[((size_t)w * P + (size_t)(3 * rows + y) * PW + 3) * 3 + xq] = 255;
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        stream_out_same_phase<2>(buf, dst, nbytes, tid);
     }
+    if (tid == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -507,7 +629,7 @@ __global__ void __launch_bounds__(256) cw_render_alt_kernel(const CwConfig cfg, 
 // ------------------------------------------------------------------------------------------------------
 struct OccEntry { size_t smem; int per_sm; };
 struct KernelInfo { bool attr_set = false; int max_dyn = 0; int n_occ = 0; OccEntry occ[64]; };   // per kernel instantiation
-struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; KernelInfo k[2]; };
+struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool alt_attr_set = false; KernelInfo k[2]; };
 static DeviceInfo g_dev[64];
 static std::mutex g_dev_mu;   // guards the per-device attribute / occupancy cache (entry points may be called from several host threads)
 
@@ -531,7 +653,7 @@ static int device_info(DeviceInfo** out) {
 
 static int check_config(const CwConfig* cfg) {
     if (!cfg) return CW_E_NULLPTR;
-    if (cfg->H < 1 || cfg->W < 1 || cfg->H > CW_MAX_SIDE || cfg->W > CW_MAX_SIDE) return CW_E_BADCONFIG;
+    if (cfg->H < 2 || cfg->W < 2 || cfg->H > CW_MAX_SIDE || cfg->W > CW_MAX_SIDE) return CW_E_BADCONFIG;   // (the reciprocal-multiply divisions need a divisor >= 2)
     if (cfg->cell_stride != (cfg->H * cfg->W + 15) / 16 * 16) return CW_E_BADCONFIG;
     if (cfg->max_steps < 1) return CW_E_BADCONFIG;
     if (cfg->n_selected < 1 || cfg->n_selected > 9) return CW_E_BADCONFIG;
@@ -809,11 +931,17 @@ int cw_onehot(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, u
     if (!grid || !agent || !onehot) return CW_E_NULLPTR;
     DeviceInfo* dev;
     rc = device_info(&dev); if (rc) return rc;
-    const int64_t n_words = n * cfg->H * cfg->W * 3;
-    int64_t blocks = (n_words + 255) / 256;
-    const int64_t cap = (int64_t)dev->sms * 16;
-    if (blocks > cap) blocks = cap;
-    cw_onehot_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, grid, agent, (uint32_t*)onehot, n_words);
+    const int64_t n_cells = n * cfg->H * cfg->W;
+    if ((uintptr_t)onehot & 3u) {                                 // foreign, unaligned buffer: byte-wise path
+        int64_t blocks = (n_cells + 255) / 256;
+        if (blocks > (int64_t)dev->sms * 16) blocks = (int64_t)dev->sms * 16;
+        cw_onehot_unaligned_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, grid, agent, onehot, n_cells);
+        return (int)cudaGetLastError();
+    }
+    const int64_t items = (n_cells + kOneHotCells - 1) / kOneHotCells;
+    int64_t blocks = items < (int64_t)dev->sms * 5 ? items : (int64_t)dev->sms * 5;   // 2 x 21.5 KB stages: 5 CTAs per SM
+    const uint32_t hw_magic = (uint32_t)(0x100000000ull / (uint64_t)(cfg->H * cfg->W)) + 1u;
+    cw_onehot_kernel<<<(unsigned)blocks, kExpThreads, 2 * kOneHotStage, (cudaStream_t)stream>>>(*cfg, grid, agent, onehot, n_cells, hw_magic);
     return (int)cudaGetLastError();
 }
 
@@ -822,13 +950,36 @@ int cw_render_alt(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agen
     if (n < 0) return CW_E_BADCONFIG;
     if (n == 0) return 0;
     if (!grid || !agent || !obs) return CW_E_NULLPTR;
+    if ((uintptr_t)obs & 1u) return CW_E_BADCONFIG;
     DeviceInfo* dev;
     rc = device_info(&dev); if (rc) return rc;
-    const int64_t n_pixels = n * (3 * cfg->H + 3) * 3 * cfg->W;
-    int64_t blocks = (n_pixels + 255) / 256;
-    const int64_t cap = (int64_t)dev->sms * 16;
-    if (blocks > cap) blocks = cap;
-    cw_render_alt_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, grid, agent, obs, n_pixels);
+    const uint32_t row_bytes = 3u * 3u * (uint32_t)cfg->W * 6u;   // one row of cells = 3 pixel rows
+    const uint32_t strip_bytes = row_bytes;                       // the status strip is 3 pixel rows too
+    const uint32_t world_bytes = row_bytes * (uint32_t)cfg->H + strip_bytes;
+    AltPlan plan;
+    if (world_bytes <= kAltBudget) {
+        plan.worlds_per_item = (int)(kAltBudget / world_bytes); if (plan.worlds_per_item > 16) plan.worlds_per_item = 16;
+        plan.bands = 1; plan.rows_per_band = cfg->H;
+        plan.items = (n + plan.worlds_per_item - 1) / plan.worlds_per_item;
+    } else {
+        plan.worlds_per_item = 1;
+        plan.rows_per_band = (int)((kAltBudget - strip_bytes) / row_bytes); if (plan.rows_per_band < 1) plan.rows_per_band = 1;
+        plan.bands = (cfg->H + plan.rows_per_band - 1) / plan.rows_per_band;
+        plan.items = n * plan.bands;
+    }
+    plan.w_magic = (uint32_t)(0x100000000ull / (uint64_t)cfg->W) + 1u;
+    const uint32_t band_cells = (uint32_t)(plan.bands == 1 ? cfg->H : plan.rows_per_band) * (uint32_t)cfg->W;
+    plan.cells_magic = (uint32_t)(0x100000000ull / (uint64_t)band_cells) + 1u;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        if (!dev->alt_attr_set) {                                 // 2 stages x 32 KB: above the 48 KB default
+            cudaError_t e = cudaFuncSetAttribute(cw_render_alt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kAltStage));
+            if (e != cudaSuccess) return (int)e;
+            dev->alt_attr_set = true;
+        }
+    }
+    int64_t blocks = plan.items < (int64_t)dev->sms * 3 ? plan.items : (int64_t)dev->sms * 3;
+    cw_render_alt_kernel<<<(unsigned)blocks, kExpThreads, 2 * kAltStage, (cudaStream_t)stream>>>(*cfg, grid, agent, obs, n, plan);
     return (int)cudaGetLastError();
 }
 

@@ -42,7 +42,7 @@ extern "C" {
 #define CW_STATS_LEN 24
 #define CW_STATS_REPLICAS 16 /* the stats buffer is int64[CW_STATS_REPLICAS][CW_STATS_LEN]: finished episodes are added to
                                 replica (block index % 16) so same-address atomics do not serialise; consumers sum the replicas */
-#define CW_MAX_SIDE 64 /* H, W <= 64 (cell_stride <= 4096) */
+#define CW_MAX_SIDE 64 /* 2 <= H, W <= 64 (cell_stride <= 4096) */
 #define CW_CHAIN_MAX_POS 1024 /* chained launches: positions 0..1023; the chain buffer is uint32[CW_CHAIN_MAX_POS + N] */
 #define CW_FRESH_WORDS 18 /* delta transport: uint32 words of a re-seeded world's sparse record (see cw_step_delta) */
 

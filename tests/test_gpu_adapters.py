@@ -125,6 +125,54 @@ def test_altobs_env_matches_reference_frames_and_oracle(cw):
     assert stacked.reset().shape == (4, 4, 21, 18, 3)
 
 
+def _random_compact_state(N, size, seed):
+    """dense random worlds (p=0.5 per cell, uniform object type), random agent cell and held item"""
+    rng = np.random.RandomState(seed)
+    stride = (size * size + 15) // 16 * 16
+    grid = np.zeros((N, stride), np.uint8)
+    cells = rng.randint(0, 9, (N, size * size)) * (rng.rand(N, size * size) < 0.5)
+    grid[:, :size * size] = cells
+    r, c, h = rng.randint(0, size, N), rng.randint(0, size, N), rng.randint(0, 4, N)
+    h[: max(1, N // 3)] = grid[np.arange(N), r * size + c][: max(1, N // 3)].clip(0, 3)   # held item == object under the agent: multiplicity 2
+    agent = (r | (c << 8) | (h << 16)).astype(np.int32)
+    return grid, agent, r, c, h
+
+
+@pytest.mark.parametrize("N,size", [(1, 5), (3, 7), (37, 8), (100, 21), (9, 32), (5, 40), (3, 64), (4099, 21)])
+def test_onehot_and_altobs_kernels_match_oracle_on_dense_states(cw, N, size):
+    """cw_onehot / cw_render_alt (staged, aligned copy-out; work items of several worlds or bands of one world) on dense random
+    states of every regime: tiny worlds packed per item, 21x21, worlds split into bands (40x40, 64x64), ragged tails."""
+    grid, agent, r, c, h = _random_compact_state(N, size, 1000 + N + size)
+    env = cw.BatchedCraftingWorldEnvAltObs(N, size=(size, size), seed=0)
+    g, a = torch.from_numpy(grid).cuda(), torch.from_numpy(agent).cuda()
+    oh = env.onehot(grid=g, agent=a).cpu().numpy()
+    alt = env.render_alt(g, a).cpu().numpy()
+    check = range(N) if N <= 128 else list(range(0, N, 97)) + [N - 1]
+    for n in check:
+        g2 = grid[n, :size * size].reshape(size, size)
+        assert np.array_equal(oh[n], ref_shim.compact_to_onehot(g2, int(r[n]), int(c[n]), int(h[n])).astype(np.uint8)), n
+        assert np.array_equal(alt[n], compact.render_alt(g2, int(r[n]), int(c[n]), int(h[n]))), n
+    # an output carved at every 2- / 4-byte phase of a 16-byte line: the head / tail paths of the copy-out
+    for phase in (4, 8, 12):
+        raw = torch.full((oh.size + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        view = raw[phase:phase + oh.size]
+        env._lib.cw_onehot(__import__("ctypes").byref(env.cfg), g.data_ptr(), a.data_ptr(), view.data_ptr(), N, torch.cuda.current_stream().cuda_stream)
+        assert np.array_equal(view.cpu().numpy().reshape(oh.shape), oh), phase
+        assert bool((raw[:phase] == 0xA5).all()) and bool((raw[phase + oh.size:] == 0xA5).all()), phase
+    for phase in (2, 6, 10, 14):
+        nb = alt.size * 2
+        raw = torch.full((nb + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        view = raw[phase:phase + nb]
+        env._lib.cw_render_alt(__import__("ctypes").byref(env.cfg), g.data_ptr(), a.data_ptr(), view.data_ptr(), N, torch.cuda.current_stream().cuda_stream)
+        assert np.array_equal(view.cpu().numpy().view(np.int16).reshape(alt.shape), alt), phase
+        assert bool((raw[:phase] == 0xA5).all()) and bool((raw[phase + nb:] == 0xA5).all()), phase
+    # unaligned one-hot output: the byte-wise fallback
+    raw = torch.full((oh.size + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+    view = raw[3:3 + oh.size]
+    env._lib.cw_onehot(__import__("ctypes").byref(env.cfg), g.data_ptr(), a.data_ptr(), view.data_ptr(), N, torch.cuda.current_stream().cuda_stream)
+    assert np.array_equal(view.cpu().numpy().reshape(oh.shape), oh)
+
+
 def test_vector_env_facade(cw):
     venv = cw.CraftingWorldVectorEnv(32, size=(5, 5), max_steps=6, seed=3)
     obs, info = venv.reset(seed=3)
