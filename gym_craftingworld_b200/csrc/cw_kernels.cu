@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
 constexpr int kExpThreads = 256;
 constexpr int kOneHotIters = 7;
 constexpr uint32_t kOneHotCells = kOneHotIters * kExpThreads;    // cells per work item (21 KB of output)
-constexpr uint32_t kOneHotStage = kOneHotCells * 12 + 32;
+constexpr uint32_t kOneHotStage = kOneHotCells * 12 + 64;   // + phase + the unused cells of a last partial quad
 constexpr uint32_t kAltBudget = 32 * 1024;       // bytes of AltObs output per work item
 constexpr uint32_t kAltStage = kAltBudget + 48;
 constexpr int kAltIters = 3;                     // cells per item <= kAltBudget / 54 = 606 <= 3 x 256
@@ -475,54 +475,89 @@ __device__ __forceinline__ void stream_out_same_phase(const uint8_t* s, uint8_t*
 }
 
 // observation_vector (ray.py:94-98, 605-613): uint8[N][H][W][12].  A work item is kOneHotCells consecutive cells of the
-// flattened (world, cell) index; a thread builds the three 32-bit words of a cell's 12 channel bytes in registers.
+// flattened (world, cell) index; a thread owns QUADS of 4 consecutive cells = 48 output bytes = three 16-byte words built in
+// registers (one index division per quad; a quad crosses at most one world boundary because H*W >= 4).
 __global__ void __launch_bounds__(kExpThreads) cw_onehot_kernel(const CwConfig cfg, const uint8_t* __restrict__ grid,
                                                                 const uint32_t* __restrict__ agent, uint8_t* __restrict__ out,
-                                                                int64_t n_cells, uint32_t hw_magic) {
+                                                                int64_t n_cells, int64_t n, uint32_t hw_magic) {
     extern __shared__ __align__(16) uint8_t xsm[];
-    const uint32_t HW = (uint32_t)(cfg.H * cfg.W);
+    const uint32_t HW = (uint32_t)(cfg.H * cfg.W), W = (uint32_t)cfg.W;
     const int tid = threadIdx.x;
     const int64_t items = (n_cells + kOneHotCells - 1) / kOneHotCells;
+    constexpr int kQuadIters = (kOneHotCells / 4 + kExpThreads - 1) / kExpThreads;   // 2
+    struct Loaded { uint32_t code[kQuadIters][4], ag[kQuadIters][2], cell0[kQuadIters]; };
+    auto load_item = [&](int64_t it, Loaded& L) {                // all loads of an item in flight together
+        const int64_t c0 = it * kOneHotCells;
+        const uint32_t cnt = (uint32_t)min((int64_t)kOneHotCells, n_cells - c0);
+        const uint32_t nquad = (cnt + 3u) >> 2;
+        const int64_t env0 = c0 / HW;
+        const uint32_t rem0 = (uint32_t)(c0 - env0 * HW);
+#pragma unroll
+        for (int u = 0; u < kQuadIters; u++) {
+            const uint32_t q = tid + u * kExpThreads;
+            const uint32_t j0 = q < nquad ? 4u * q : 0u;
+            const uint32_t idx = rem0 + j0;
+            const uint32_t de = __umulhi(idx, hw_magic);          // idx / HW  (idx < kOneHotCells + HW)
+            const int64_t env = env0 + de;
+            L.cell0[u] = idx - de * HW;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t ci = L.cell0[u] + i;
+                const bool wrap = ci >= HW;
+                L.code[u][i] = (j0 + i < cnt) ? grid[(env + (wrap ? 1 : 0)) * cfg.cell_stride + (wrap ? ci - HW : ci)] : 0u;
+            }
+            L.ag[u][0] = agent[env];
+            L.ag[u][1] = agent[env + 1 < n ? env + 1 : env];
+        }
+    };
     int stage = 0;
+    Loaded cur, nxt;
+    if ((int64_t)blockIdx.x < items) load_item(blockIdx.x, cur);
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x, stage ^= 1) {
         const int64_t c0 = it * kOneHotCells;
         const uint32_t cnt = (uint32_t)min((int64_t)kOneHotCells, n_cells - c0);
-        const int64_t env0 = c0 / HW;
-        const uint32_t rem0 = (uint32_t)(c0 - env0 * HW);
+        const uint32_t nquad = (cnt + 3u) >> 2;
         uint8_t* dst = out + c0 * 12;
-        uint8_t* buf = xsm + stage * kOneHotStage + ((uintptr_t)dst & 15u);   // 4-byte aligned: c0 * 12 and the base pointer are
-        uint32_t code[kOneHotIters], ag[kOneHotIters], cell[kOneHotIters];
-#pragma unroll
-        for (int u = 0; u < kOneHotIters; u++) {                  // all loads of the item in flight together
-            const uint32_t j = tid + u * kExpThreads;
-            const uint32_t idx = rem0 + (j < cnt ? j : 0u);
-            const uint32_t de = __umulhi(idx, hw_magic);          // idx / HW  (idx < kOneHotCells + HW)
-            const int64_t env = env0 + de;
-            cell[u] = idx - de * HW;
-            code[u] = grid[env * cfg.cell_stride + cell[u]];
-            ag[u] = agent[env];
-        }
+        const uint32_t phase = (uint32_t)((uintptr_t)dst & 15u);  // 0, 4, 8 or 12 (c0 * 12 is a multiple of 16)
+        uint8_t* buf = xsm + stage * kOneHotStage + phase;
+        if (it + gridDim.x < items) load_item(it + gridDim.x, nxt);   // next item's loads fly while this one is composed
         if (tid == 0) bulk_wait_read<1>();                        // the store that last read this stage has drained
         __syncthreads();
 #pragma unroll
-        for (int u = 0; u < kOneHotIters; u++) {
-            const uint32_t j = tid + u * kExpThreads;
-            if (j >= cnt) continue;
-            const uint32_t acell = (ag[u] & 0xFF) * (uint32_t)cfg.W + ((ag[u] >> 8) & 0xFF);
-            uint32_t w0 = 0, w1 = 0, w2 = 0;
-            if (code[u] >= 1 && code[u] <= 4) w0 = 1u << (8 * (code[u] - 1));        // object channels 0..3
-            else if (code[u] >= 5 && code[u] <= 8) w1 = 1u << (8 * (code[u] - 5));   // object channels 4..7
-            if (cell[u] == acell) {
-                w2 = 1u;                                                             // channel 8: agent
-                const uint32_t h = (ag[u] >> 16) & 0xFF;
-                if (h >= 1 && h <= 3) w2 |= 1u << (8 * h);                           // channels 9..11: holding
+        for (int u = 0; u < kQuadIters; u++) {
+            const uint32_t q = tid + u * kExpThreads;
+            if (q >= nquad) continue;
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t ci = cur.cell0[u] + i;
+                const bool wrap = ci >= HW;
+                const uint32_t cell = wrap ? ci - HW : ci, a = wrap ? cur.ag[u][1] : cur.ag[u][0], cd = cur.code[u][i];
+                const uint32_t acell = (a & 0xFF) * W + ((a >> 8) & 0xFF);
+                const uint32_t bit = 1u << (8 * ((cd - 1u) & 3u));
+                w[3 * i + 0] = (cd >= 1 && cd <= 4) ? bit : 0u;   // object channels 0..3
+                w[3 * i + 1] = (cd >= 5 && cd <= 8) ? bit : 0u;   // object channels 4..7
+                uint32_t w2 = 0;
+                if (cell == acell) {
+                    const uint32_t h = (a >> 16) & 0xFF;
+                    w2 = 1u | ((h >= 1 && h <= 3) ? 1u << (8 * h) : 0u);   // channel 8: agent; 9..11: holding
+                }
+                w[3 * i + 2] = w2;
             }
-            uint32_t* p = reinterpret_cast<uint32_t*>(buf) + 3 * j;
-            p[0] = w0; p[1] = w1; p[2] = w2;
+            uint8_t* p = buf + 48u * q;
+            if (phase == 0) {
+                reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                reinterpret_cast<uint4*>(p)[2] = make_uint4(w[8], w[9], w[10], w[11]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 12; k++) reinterpret_cast<uint32_t*>(p)[k] = w[k];
+            }
         }
         fence_proxy_async_smem();
         __syncthreads();
         stream_out_same_phase<4>(buf, dst, cnt * 12, tid);
+        cur = nxt;
     }
     if (tid == 0) bulk_wait_all();
 }
@@ -941,7 +976,7 @@ int cw_onehot(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, u
     const int64_t items = (n_cells + kOneHotCells - 1) / kOneHotCells;
     int64_t blocks = items < (int64_t)dev->sms * 5 ? items : (int64_t)dev->sms * 5;   // 2 x 21.5 KB stages: 5 CTAs per SM
     const uint32_t hw_magic = (uint32_t)(0x100000000ull / (uint64_t)(cfg->H * cfg->W)) + 1u;
-    cw_onehot_kernel<<<(unsigned)blocks, kExpThreads, 2 * kOneHotStage, (cudaStream_t)stream>>>(*cfg, grid, agent, onehot, n_cells, hw_magic);
+    cw_onehot_kernel<<<(unsigned)blocks, kExpThreads, 2 * kOneHotStage, (cudaStream_t)stream>>>(*cfg, grid, agent, onehot, n_cells, n, hw_magic);
     return (int)cudaGetLastError();
 }
 
