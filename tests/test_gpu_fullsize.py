@@ -70,6 +70,65 @@ def test_config2_4096_worlds_full_episode(cw):
     assert np.array_equal(env.stats.cpu().numpy(), ob.stats) and ob.stats[0] >= N
 
 
+def test_config2_chained_graph_full_episode(cw):
+    """Config 2 exactly as bench.py runs it: 330 steps captured as ONE chain of launches (cw_step_render_chained) in a CUDA
+    graph, frames rotating over 4 buffers -- final state, statistics, goal / init frames and the last 4 frames of every world
+    against the oracle."""
+    N, seed, K, R = 4096, 2, 330, 4
+    env = cw.BatchedCraftingWorldEnv(N, seed=seed, auto_reset=True, obs_buffers=R)
+    ob = oracle_like(env, seed)
+    env.reset()
+    o_goal = ob.reset(with_goal=True)
+    o_obs = ob.render()
+    o_init = o_obs.copy()
+    acts = torch.randint(0, 6, (K, N), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+    acts_np, acts_gpu = acts.numpy(), acts.cuda()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for k in range(K):
+                env.step(acts_gpu[k], chain_pos=k)
+        g.replay()
+    new_goal = np.zeros_like(o_goal)
+    last = {}
+    for k in range(K):
+        _, o_done = ob.step_full(acts_np[k], auto_reset=True, obs=o_obs, goal_obs=new_goal)
+        fresh = o_done == 1
+        if fresh.any():
+            o_goal[fresh] = new_goal[fresh]
+            o_init[fresh] = o_obs[fresh]
+        if k >= K - R:
+            last[k] = o_obs.copy()
+    torch.cuda.synchronize()
+    assert state_equal(env, ob) and np.array_equal(env.stats.cpu().numpy(), ob.stats) and ob.stats[0] >= N
+    assert np.array_equal(env.desired_goal.cpu().numpy(), o_goal) and np.array_equal(env.init_obs.cpu().numpy(), o_init)
+    for k in range(K - R, K):                                      # step k wrote ring buffer (k + 1) % R
+        assert np.array_equal(env._obs_ring[(k + 1) % R].cpu().numpy(), last[k]), f"frames of step {k}"
+
+
+def test_config4_chained_131072_worlds(cw):
+    """Config 4 per-GPU slice through chained launches (persistent CTAs, 2 frame buffers): state + statistics bit-exact against
+    the oracle, every pixel of the last two steps against a fresh render of the corresponding state."""
+    N, seed, K = 131072, 6, 12
+    env = cw.BatchedCraftingWorldEnv(N, max_steps=10, seed=seed, auto_reset=True, goal_images=False, obs_buffers=2)
+    ref = cw.BatchedCraftingWorldEnv(N, max_steps=10, seed=seed, auto_reset=True, goal_images=False)
+    ob = oracle_like(env, seed)
+    env.reset(); ref.reset(); ob.reset()
+    acts = np.random.RandomState(9).randint(0, 6, (K, N)).astype(np.uint8)
+    a_gpu = torch.from_numpy(acts).cuda()
+    for k in range(K):
+        env.step(a_gpu[k], chain_pos=k)
+        ob.step_full(acts[k], auto_reset=True)
+    for k in range(K - 1):
+        ref.step(a_gpu[k])
+    assert torch.equal(env._obs_ring[(K - 1) % 2], ref.obs)         # step K-2
+    ref.step(a_gpu[K - 1])
+    assert torch.equal(env._obs_ring[K % 2], ref.obs)               # step K-1
+    assert state_equal(env, ob) and np.array_equal(env.stats.cpu().numpy(), ob.stats) and ob.stats[0] > N
+
+
 def test_config5_16384_dense_32x32(cw):
     """Config 5: 16384 dense 32x32 worlds -- 24 fused steps; final state and EVERY pixel (805 MB) against the oracle."""
     N, H, seed, K = 16384, 32, 3, 24
