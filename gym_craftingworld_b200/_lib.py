@@ -18,7 +18,7 @@ F_AUTO_RESET = 1
 F_DELTA_TRANSPORT = 2
 
 # every symbol include/cw_b200.h declares (tests check the library exports exactly these)
-SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_step_render_chained", "cw_step_delta", "cw_rollout",
+SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_step_render_chained", "cw_step_render_edit", "cw_step_delta", "cw_rollout",
            "cw_imagine", "cw_onehot", "cw_render_alt", "cw_host_create", "cw_host_reset", "cw_host_step", "cw_host_stats",
            "cw_host_device_state", "cw_host_destroy"]
 
@@ -55,6 +55,7 @@ def _declare(lib):
         "cw_step": [cfgp, stp, vp, vp, vp, vp, ci, vp],
         "cw_render": [cfgp, vp, vp, vp, i64, vp],
         "cw_step_render": [cfgp, stp, vp, vp, vp, vp, vp, vp, vp, ci, vp],
+        "cw_step_render_edit": [cfgp, stp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp],
         "cw_step_render_chained": [cfgp, stp, vp, vp, vp, vp, vp, vp, vp, ci, vp, ci, ci, vp],
         "cw_rollout": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
         "cw_step_delta": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],

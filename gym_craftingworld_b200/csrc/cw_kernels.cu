@@ -34,6 +34,7 @@ struct EnvArgs {
     unsigned long long* stats;
     uint4* delta;            // delta transport: per-world record {agent, goal, wcell | wval<<16 | flags<<24, reward} (nullable)
     uint32_t* fresh;         // delta transport: [N][CW_FRESH_WORDS] sparse record of a re-seeded world + its imagined goal
+    uint32_t* list;          // work-list launch (cw_step_render_edit): [0] count, [1] exit ticket, [2..] world ids to re-seed
     uint32_t delta_seq;      // delta transport: 6-bit sequence tag stored in bits 2..7 of the record's flag byte
     const uint8_t* rgrid;    // render-only entry: grid / agent given directly (state may be partial)
     const uint32_t* ragent;
@@ -101,15 +102,17 @@ enum : int { BAR_COMPOSE = 1, BAR_RESET_DONE = 2 };
 // dynamic shared memory: [tiles 2 x G x cell_stride][imagine scratch G x cell_stride][ring F x chunk_bytes]
 // kChained = false is the ordinary launch; true adds the chain protocol (a separate instantiation, so the ordinary
 // launch's code is exactly what it was -- the extra control flow measurably slowed it when it shared one body).
-template <bool kChained>
+enum : int { V_PLAIN = 0, V_CHAINED = 1, V_LIST = 2 };
+template <int kVariant>
 __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
+    constexpr bool kChained = kVariant == V_CHAINED, kList = kVariant == V_LIST;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_lut[9];
     __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32], s_ep[32], s_rew[32];
     __shared__ uint32_t s_flag[32];
     __shared__ uint32_t s_obj[8];
     __shared__ uint32_t s_anypend;
-    __shared__ uint32_t s_pre[kChained ? 5 : 1][32];              // chained: next group's scalars, parked by the reset warp
+    __shared__ uint32_t s_pre[kVariant == V_CHAINED ? 5 : 1][32];              // chained: next group's scalars, parked by the reset warp
 
     const int H = cfg.H, W = cfg.W, cs = cfg.cell_stride;
     const int G = args.group, F = args.nbuf, mode = args.mode;
@@ -124,7 +127,9 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     const int nchunk16 = cs >> 4;
     const uint8_t* grid_in = args.rgrid ? args.rgrid : st.grid;
     const uint32_t* agent_in = args.ragent ? args.ragent : st.agent;
-    const int64_t ngroups = (st.n + G - 1) / G;
+    int64_t ngroups = (st.n + G - 1) / G;
+    // a pure (masked) reset overwrites the tiles of the worlds it touches and skips the others: nothing to load
+    const bool need_tiles = (mode & (M_STEP | M_IMAGINE_ONLY)) || !(mode & M_FORCE_RESET);
     // Chained launch (cw_step_render_chained, position > 0): the previous launch in the stream is the same kernel on the
     // same worlds, one chain position earlier.  Instead of waiting for that whole grid (and for its frame stores to
     // drain), a CTA waits per GROUP for the predecessor's state of exactly the worlds it is about to step (epoch word,
@@ -144,18 +149,24 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     if (tid < 9) s_lut[tid] = kColorLUT[tid];
     if (!chain_follow) pdl_wait();
     CW_STAMP(1);
+    // work-list launch: one world per CTA iteration (G == 1), the worlds are the ids the preceding step launch appended
+    if (kList) ngroups = (int64_t)__ldcg(args.list);
+    auto first_world = [&](int64_t g) -> int64_t { return kList ? (int64_t)__ldcg(args.list + 2 + g) : g * G; };
 
     // tile + scalar prefetch of group `g` (tiles -> stage `sgi`; scalars -> registers of warp 0).  Ordinary launches:
     // issued by all threads at the top of the iteration before.
     uint32_t p_agent = 0, p_goal = 0, p_ep = 0;
     int p_t = 0, p_a = 6, p_forced = 0;
+    int64_t p_e0 = 0;
     auto prefetch = [&](int64_t g, int sgi) {
         if (g < ngroups) {
-            const int64_t e0 = g * G;
+            const int64_t e0 = first_world(g);
+            p_e0 = e0;
             const int cnt = (int)min((int64_t)G, st.n - e0);
             const uint8_t* src = grid_in + e0 * cs;
             uint8_t* dst = tiles + (size_t)sgi * G * cs;
-            for (int i = tid; i < cnt * nchunk16; i += kEnvThreads) cp_async16(dst + 16 * i, src + 16 * i);
+            if (need_tiles)
+                for (int i = tid; i < cnt * nchunk16; i += kEnvThreads) cp_async16(dst + 16 * i, src + 16 * i);
             if (tid < cnt) {                                      // L2 loads (.cg): streaming, no reuse in L1
                 const int64_t e = e0 + tid;
                 p_agent = __ldcg(agent_in + e);
@@ -229,6 +240,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
         uint32_t c_agent = p_agent, c_goal = p_goal, c_ep = p_ep;
         int c_t = p_t, c_a = p_a;
         const int c_forced = p_forced;
+        const int64_t c_e0 = p_e0;
         if constexpr (kChained) {
             cp_async_wait<0>();                                   // (reset warp) this group's tiles have landed
         } else {
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
         }
         CW_STAMP(2);
         uint8_t* gt = tiles + (size_t)stage * G * cs;             // this group's tiles
-        const int64_t e0 = gi * G;
+        const int64_t e0 = kList ? c_e0 : gi * G;
         // ---- B: warp 0 steps the group lane-parallel -------------------------------------------------------------
         if (tid < 32) {
             const int lane = tid;
@@ -392,15 +404,63 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     if (tid == 0) {
         bulk_wait_all();
         if (chained) { __threadfence(); atomicAdd(c_fin + cpos, 1u); }   // this CTA's frames of chain position cpos are complete
+        if (kList) {                                              // the last CTA out (all have read the count) empties the list
+            __threadfence();
+            if (atomicAdd(args.list + 1, 1u) == gridDim.x - 1) { args.list[0] = 0; args.list[1] = 0; }
+        }
     }
     if (chain_follow) pdl_wait();                                 // do not COMPLETE before the predecessor grid has
     CW_STAMP(7);
 }
 
 // one thread per world, K steps per launch (K = 1: cw_step; K > 1: cw_rollout)
+// render_edit (ray.py:522-557) on the device frame of one world: the <= 2 cells a step can change.  A cell whose OBJECT
+// is unchanged differs only in the centred 2x2 overlay block (two 6-byte spans at byte offset 3 of the cell's rows 1, 2);
+// the cell the step wrote (always the agent's cell) is rewritten in full.  `frame` is 16-byte aligned, a row 12*W bytes.
+__device__ __forceinline__ void span6(uint8_t* p, uint32_t rgb) {   // R G B R G B at p, p % 4 == 3
+    p[0] = (uint8_t)rgb;
+    *reinterpret_cast<uint32_t*>(p + 1) = __byte_perm(rgb, 0, 0x1021);   // G B R G
+    p[5] = (uint8_t)(rgb >> 16);
+}
+__device__ __forceinline__ void frame_edit(const CwConfig& cfg, uint8_t* frame, const uint8_t* g, uint32_t old_agent, uint32_t agent,
+                                           int wcell, int wval) {
+    const int W = cfg.W;
+    const size_t rowb = (size_t)12 * W;
+    const int orow = old_agent & 0xFF, ocol = (old_agent >> 8) & 0xFF;
+    const int nrow = agent & 0xFF, ncol = (agent >> 8) & 0xFF, hold = (agent >> 16) & 0xFF;
+    const int oc = orow * W + ocol, nc = nrow * W + ncol;
+    uint8_t* pn = frame + (size_t)(4 * nrow) * rowb + 12 * ncol;
+    if (oc != nc) {                                               // the agent left `oc`; the object there did not change
+        uint8_t* po = frame + (size_t)(4 * orow) * rowb + 12 * ocol;
+        const uint32_t rgb = kColorLUT[g[oc]];
+        span6(po + rowb + 3, rgb); span6(po + 2 * rowb + 3, rgb);
+    }
+    if (wcell == nc) {                                            // the object under the agent changed: all four rows
+        const uint32_t rgb = kColorLUT[wval];
+        const uint32_t w0 = __byte_perm(rgb, 0, 0x0210), w1 = __byte_perm(rgb, 0, 0x1021), w2 = __byte_perm(rgb, 0, 0x2102);
+#pragma unroll
+        for (int y = 0; y < 4; y += 3) {                          // rows 0 and 3 in full; rows 1, 2 get their outer pixels
+            uint32_t* q = reinterpret_cast<uint32_t*>(pn + y * rowb);
+            q[0] = w0; q[1] = w1; q[2] = w2;
+        }
+#pragma unroll
+        for (int y = 1; y < 3; y++) {
+            uint8_t* q = pn + y * rowb;
+            q[0] = (uint8_t)rgb; q[1] = (uint8_t)(rgb >> 8); q[2] = (uint8_t)(rgb >> 16);
+            q[9] = (uint8_t)rgb; q[10] = (uint8_t)(rgb >> 8); q[11] = (uint8_t)(rgb >> 16);
+        }
+    }
+    span6(pn + rowb + 3, 0x00FFFFFFu);                            // ray.py:555
+    span6(pn + 2 * rowb + 3, hold ? kColorLUT[hold] : 0x00FFFFFFu);   // ray.py:556-557
+}
+
+// one thread per world, K steps per launch (K = 1: cw_step; K > 1: cw_rollout).  `obs` (nullable): the world's device frame is
+// kept current by render_edit.  CW_F_DEFER_RESET: a finished world is counted and reported but NOT re-seeded here (the caller
+// follows up with a masked cw_reset, which also renders the new episode's frames).
+template <bool kEdit>   // (a separate instantiation: the frame patching must not cost the compact path registers)
 __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
                                                       int32_t* __restrict__ reward, uint8_t* __restrict__ done,
-                                                      unsigned long long* stats, int K, int flags) {
+                                                      unsigned long long* stats, uint8_t* obs, uint32_t* list, int K, int flags) {
     CW_WSTAMP(0);
     pdl_launch_dependents();
     pdl_wait();
@@ -412,18 +472,30 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
     const uint8_t* ig = st.init_grid + nn * cfg.cell_stride;
     uint32_t agent = 0, goal = 0, ep = 0;
     int t = 0;
-    if (valid) { agent = st.agent[n]; goal = st.goal[n]; t = st.t[n]; ep = (flags & CW_F_AUTO_RESET) ? st.episode[n] : 0u; }
+    if (valid) { agent = st.agent[n]; goal = st.goal[n]; t = st.t[n]; ep = ((flags & CW_F_AUTO_RESET) && !(flags & CW_F_DEFER_RESET)) ? st.episode[n] : 0u; }
     for (int k = 0; k < K; k++) {
         bool dn = false;
         if (valid) {
             const int a = actions[(size_t)k * st.n + n];
             int wcell, wval;
+            const uint32_t old_agent = agent;
             const int rew = step_core(cfg, g, ig, agent, goal, t, a, dn, wcell, wval);
+            if (kEdit && (wcell >= 0 || agent != old_agent))
+                frame_edit(cfg, obs + (size_t)n * 48 * cfg.H * cfg.W, g, old_agent, agent, wcell, wval);
             if (reward) reward[(size_t)k * st.n + n] = rew;
             if (done) done[(size_t)k * st.n + n] = dn ? 1 : 0;
             if (dn && (flags & CW_F_AUTO_RESET) && stats) stats_add(cfg, stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
         }
-        if (flags & CW_F_AUTO_RESET) {                            // finished worlds are re-seeded by the whole warp
+        if (kEdit && list && (flags & CW_F_AUTO_RESET)) {          // deferred reset: queue the finished worlds (one atomic per warp)
+            const uint32_t m = __ballot_sync(0xffffffffu, valid && dn);
+            if (m) {
+                uint32_t base = 0;
+                if (lane_id() == __ffs(m) - 1) base = atomicAdd(list, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (valid && dn) list[2 + base + __popc(m & ((1u << lane_id()) - 1u))] = (uint32_t)n;
+            }
+        }
+        if (!kEdit && (flags & CW_F_AUTO_RESET) && !(flags & CW_F_DEFER_RESET)) {   // finished worlds are re-seeded by the whole warp
             uint32_t m = __ballot_sync(0xffffffffu, valid && dn);
             CW_WSTAMP(2);
 #ifdef CW_TIMING
@@ -664,7 +736,7 @@ __global__ void __launch_bounds__(kExpThreads) cw_render_alt_kernel(const CwConf
 // ------------------------------------------------------------------------------------------------------
 struct OccEntry { size_t smem; int per_sm; };
 struct KernelInfo { bool attr_set = false; int max_dyn = 0; int n_occ = 0; OccEntry occ[64]; };   // per kernel instantiation
-struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool alt_attr_set = false; KernelInfo k[2]; };
+struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool alt_attr_set = false; KernelInfo k[3]; };
 static DeviceInfo g_dev[64];
 static std::mutex g_dev_mu;   // guards the per-device attribute / occupancy cache (entry points may be called from several host threads)
 
@@ -748,8 +820,9 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     int rc = device_info(&dev);
     if (rc) return rc;
     if (st->n <= 0) return 0;
-    auto kern = args.chain ? cw_env_kernel<true> : cw_env_kernel<false>;
-    KernelInfo* ki = &dev->k[args.chain ? 1 : 0];
+    const int variant = args.chain ? V_CHAINED : (args.list ? V_LIST : V_PLAIN);
+    auto kern = variant == V_CHAINED ? cw_env_kernel<V_CHAINED> : (variant == V_LIST ? cw_env_kernel<V_LIST> : cw_env_kernel<V_PLAIN>);
+    KernelInfo* ki = &dev->k[variant];
     std::unique_lock<std::mutex> lk(g_dev_mu);
     if (!ki->attr_set) {   // once per device: allow any dynamic size up to the opt-in maximum, prefer shared memory
         cudaFuncAttributes fa;
@@ -772,7 +845,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     if (F <= 0) {
         const double frame_total = (double)st->n * 48.0 * cfg->H * cfg->W;
         const bool single_chunk = args.bands_per_chunk >= cfg->H;
-        F = (!needs_frame || !single_chunk) ? 2 : (frame_total >= 1.2e9 ? 4 : (frame_total >= 0.6e9 ? 3 : 2));
+        F = (!needs_frame || !single_chunk || args.list) ? 2 : (frame_total >= 1.2e9 ? 4 : (frame_total >= 0.6e9 ? 3 : 2));
     }
     F = F < 2 ? 2 : (F > 6 ? 6 : F);
     args.nbuf = F;
@@ -784,7 +857,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     // group size G: the per-SM critical path is (CTA waves) x G worlds; pick the G that minimises it
     int bestG = 0, best_per_sm = 1;
     int64_t best_cost = 0;
-    const int forcedG = tunables().group;
+    const int forcedG = args.list ? 1 : tunables().group;
     const int gmax = 16384 / cfg->cell_stride < 1 ? 1 : (16384 / cfg->cell_stride > 16 ? 16 : 16384 / cfg->cell_stride);
     for (int G = (forcedG > 0 ? forcedG : 1); G <= (forcedG > 0 ? forcedG : gmax); G++) {
         if (G > 32) break;
@@ -812,7 +885,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     const size_t smem = 3 * (size_t)bestG * cfg->cell_stride + ring;
     int64_t blocks = (int64_t)dev->sms * best_per_sm;
     const int64_t groups = (st->n + bestG - 1) / bestG;
-    if (blocks > groups) blocks = groups;
+    if (blocks > groups) blocks = groups;                         // (work-list launch: the count lives on the device; groups == n)
     if (args.chain && args.chain_pos == 0) {                      // a chain opens: clear its counters and epoch words
         cudaError_t me = cudaMemsetAsync(args.chain, 0, sizeof(uint32_t) * (size_t)(CW_CHAIN_MAX_POS + st->n), stream);
         if (me != cudaSuccess) return (int)me;
@@ -881,9 +954,31 @@ int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, i
     if (st->n == 0 || K == 0) return 0;
     if (!actions) return CW_E_NULLPTR;
     const int64_t blocks = (st->n + 127) / 128;
-    cudaError_t le = launch_pdl(cw_step_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions,
-                                reward, done, (unsigned long long*)stats, K, flags);
+    cudaError_t le = launch_pdl(cw_step_kernel<false>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions,
+                                reward, done, (unsigned long long*)stats, (uint8_t*)nullptr, (uint32_t*)nullptr, K, flags);
     return (int)(le != cudaSuccess ? le : cudaGetLastError());
+}
+
+int cw_step_render_edit(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done, uint8_t* obs,
+                        uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, uint32_t* scratch, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    rc = check_state(st); if (rc) return rc;
+    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
+    if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
+    if (st->n == 0) return 0;
+    if (!actions || !reward || !done || !obs) return CW_E_NULLPTR;
+    if ((flags & CW_F_AUTO_RESET) && !scratch) return CW_E_NULLPTR;
+    if (st->n > 0xFFFFFFFFll) return CW_E_BADCONFIG;
+    const int64_t blocks = (st->n + 127) / 128;
+    cudaError_t le = launch_pdl(cw_step_kernel<true>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions,
+                                reward, done, (unsigned long long*)stats, obs, scratch, 1,
+                                flags | ((flags & CW_F_AUTO_RESET) ? CW_F_DEFER_RESET : 0));
+    if (le != cudaSuccess) return (int)le;
+    if (!(flags & CW_F_AUTO_RESET)) return (int)cudaGetLastError();
+    EnvArgs a = {};                                               // reset of the queued worlds + their three frames, one world per CTA
+    a.list = scratch; a.obs = obs; a.goal_obs = goal_obs; a.init_obs = init_obs;
+    a.mode = M_FORCE_RESET | M_RENDER;
+    return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
 }
 
 int cw_render(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, uint8_t* obs, int64_t n, void* stream) {

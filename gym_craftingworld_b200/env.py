@@ -135,12 +135,17 @@ class BatchedCraftingWorldEnv:
     def __init__(self, num_envs, size=(STATE_W, STATE_H), fixed_init_state=0, max_steps=MAX_STEPS, store_gif=False,
                  render_save_rate=1, task_list=TASK_LIST, selected_tasks=TASK_LIST, number_of_tasks=None, stacking=True,
                  reward_style=None, *, device=None, seed=None, auto_reset=True, obs_mode="pixels", env_id_base=0,
-                 goal_images=True, obs_buffers=1, validate_actions=False, collect_stats=True):
+                 goal_images=True, obs_buffers=1, validate_actions=False, collect_stats=True, render="full"):
         if store_gif:
             raise NotImplementedError("GIF recording (ray.py:565-597, 769-782) is a host-side debugging side channel; "
                                       "out of scope (DESIGN.md)")
         if obs_mode not in ("pixels", "compact", "onehot"):
             raise ValueError("obs_mode must be 'pixels', 'compact' or 'onehot'")
+        if render not in ("full", "incremental"):
+            raise ValueError("render must be 'full' (every frame re-expanded every step) or 'incremental' (render_edit)")
+        if render == "incremental" and (obs_mode != "pixels" or int(obs_buffers) != 1):
+            raise ValueError("render='incremental' patches ONE persistent frame buffer: needs obs_mode='pixels', obs_buffers=1")
+        self.render_mode = render
         self.num_envs = int(num_envs)
         if self.num_envs < 1:
             raise ValueError("num_envs must be >= 1")
@@ -205,6 +210,7 @@ class BatchedCraftingWorldEnv:
             self.init_agent = torch.zeros(N, dtype=torch.int32, device=dev)
         self._obs_version = 0
         self._chain = None                        # chain words of cw_step_render_chained (allocated on first use)
+        self._edit_scratch = None                 # work list of cw_step_render_edit (allocated on first use)
         self._fixed_grid = self._fixed_agent = None
         self._seed = None
         self._state = _lib.CwState()
@@ -385,6 +391,18 @@ class BatchedCraftingWorldEnv:
                 if len(self._obs_ring) > 1:
                     self._ring_pos = (self._ring_pos + 1) % len(self._obs_ring)
                     self.obs = self._obs_ring[self._ring_pos]
+                if self.render_mode == "incremental":         # the reference's render_edit: patch the <= 2 changed cells
+                    if chain_pos is not None:
+                        raise ValueError("chain_pos applies to render='full' only")
+                    if self._edit_scratch is None:
+                        self._edit_scratch = torch.zeros(self.num_envs + 2, dtype=torch.int32, device=self.device)
+                    rc = self._lib.cw_step_render_edit(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                                                       self._done_u8.data_ptr(), self.obs.data_ptr(), self._ptr(self.desired_goal),
+                                                       self._ptr(self.init_obs), self._stats_ptr(), flags,
+                                                       self._edit_scratch.data_ptr(), self._stream())
+                    _lib.check(rc, "cw_step_render_edit")
+                    self._obs_version += 1
+                    return self._observation(), self.reward, self.done, self._info
                 if chain_pos is not None:
                     if self._chain is None:
                         self._chain = torch.zeros(_lib.CHAIN_MAX_POS + self.num_envs, dtype=torch.int32, device=self.device)

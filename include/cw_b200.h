@@ -55,6 +55,7 @@ extern "C" {
 /* flags */
 #define CW_F_AUTO_RESET 1 /* on done: add the episode to stats, Philox-reset the world in the same launch; the
                              returned reward/done are the finished episode's, state/obs the new episode's */
+#define CW_F_DEFER_RESET 8 /* internal (cw_step_render_edit): count and report a finished world but do not re-seed it in the step launch */
 #define CW_F_DELTA_TRANSPORT 2 /* cw_host_create only: keep the caller's frame buffer current by delta records + host-side
                                   patching of the changed cells instead of copying every frame over PCIe */
 
@@ -121,6 +122,18 @@ int cw_render(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, u
  * obs may be NULL (no pixels: step + auto-reset + the compact goal outputs of CwState only). */
 int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
                    uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, void* stream);
+
+/* step + auto-reset with INCREMENTAL rendering -- the reference's own algorithm (`render_edit`, ray.py:522-557, called from
+ * step at ray.py:358): `obs` is a persistent frame buffer (the same pointer every call, last written by cw_reset / cw_render /
+ * this function) and only the <= 2 cells a step changes are rewritten in it, by the thread that steps the world; worlds that
+ * finish are queued and re-seeded by a second launch (one world per CTA) that renders their new obs / goal_obs / init_obs frames.
+ * After the call `obs` holds exactly what cw_step_render would have written.  HBM traffic per env-step drops from 48*H*W bytes
+ * to a few sectors, so this path is latency- not bandwidth-bound.
+ * `scratch` (device uint32[N + 2], zeroed once by the caller, needed with CW_F_AUTO_RESET): the work list of finished worlds
+ * that links the two launches; the library leaves it empty again after every call. */
+int cw_step_render_edit(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
+                        uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, uint32_t* scratch,
+                        void* stream);
 
 /* cw_step_render for an OPEN-LOOP run of steps (action tape known in advance, e.g. a CUDA graph of K steps): the same
  * launch per step, but consecutive launches are chained by per-group dataflow instead of whole-grid dependencies.

@@ -328,6 +328,47 @@ def test_step_is_cuda_graph_capturable(cw):
         assert torch.equal(getattr(env, key), getattr(ref, key)), key
 
 
+@pytest.mark.parametrize("name", gu.golden_files())
+def test_incremental_render_matches_reference_trace(cw, name):
+    """cw_step_render_edit -- the reference's own render_edit (ray.py:522-557) on the device frame: only the <= 2 changed cells
+    are rewritten each step -- reproduces the reference trace: state, reward, done and every pixel of every step."""
+    d = gu.load(name)
+    env = make_env(cw, d, render="incremental")
+    B, T = d["actions"].shape
+    fidx = {int(t): i for i, t in enumerate(d["frame_t"])}
+    for t in range(T):
+        obs, reward, done, _ = env.step(torch.from_numpy(d["actions"][:, t]).cuda())
+        where = f"{name} step {t}"
+        assert np.array_equal(reward.cpu().numpy(), d["reward"][:, t]) and np.array_equal(done.cpu().numpy(), d["done"][:, t].astype(bool)), where
+        assert_state_equals_golden(env, d, t, where)
+        frames = obs["observation"].cpu().numpy()
+        assert [gu.crc(f) for f in frames] == list(d["frame_crc"][:, t]), where
+        if t in fidx:
+            assert np.array_equal(frames, d["frames"][:, fidx[t]]), where
+
+
+@pytest.mark.parametrize("N,size,max_steps", [(700, 7, 5), (4096, 21, 40), (300, 32, 12)])
+def test_incremental_render_with_auto_reset_matches_full_render(cw, N, size, max_steps):
+    """Incremental and full rendering side by side with auto-reset: identical state, reward, done, statistics and identical
+    observation / goal / init frames after every step (the finished worlds are re-seeded by the masked reset launch)."""
+    K = 3 * max_steps + 7
+    acts = torch.from_numpy(np.random.RandomState(N).randint(0, 6, (K, N)).astype(np.uint8)).cuda()
+    full = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=17)
+    inc = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=17, render="incremental")
+    o1, o2 = full.reset(), inc.reset()
+    for key in ("observation", "desired_goal", "init_observation"):
+        assert torch.equal(o1[key], o2[key]), key
+    for k in range(K):
+        o1, r1, d1, _ = full.step(acts[k])
+        o2, r2, d2, _ = inc.step(acts[k])
+        assert torch.equal(r1, r2) and torch.equal(d1, d2), k
+        for key in ("observation", "desired_goal", "init_observation"):
+            assert torch.equal(o1[key], o2[key]), (key, k)
+    for key in ("grid", "init_grid", "agent", "goal", "t", "episode", "stats"):   # (stats: the 16 replicas are filled differently)
+        assert torch.equal(getattr(full, key), getattr(inc, key)), key
+    assert int(full.stats[0]) >= N
+
+
 @pytest.mark.parametrize("N,size,max_steps,ring,K,graph", [
     (64, 7, 3, 1, 40, True),          # tiny launches: several chain positions co-resident, one frame buffer, resets every <= 3 steps
     (300, 7, 2, 3, 48, True),         # a world can be re-seeded in consecutive positions (goal / init frames have no ring)
