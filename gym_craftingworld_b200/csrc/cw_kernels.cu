@@ -1,13 +1,18 @@
 // cw_kernels.cu -- sm_100a kernels + C-ABI launchers of the batched CraftingWorld hot path.
 //
-//   cw_env_kernel   one CTA per world (grid-stride): [step] -> [auto/forced Philox reset (+imagine_obs goal frame)]
-//                   -> render.  The world's grid tile is staged in shared memory; the RGB frame is composed in
-//                   shared memory and streamed out with TMA bulk stores (cp.async.bulk shared::cta -> global), so
-//                   the global write stream is full-line and issues no LSU store instructions.
-//                   Bound: HBM write bandwidth (48*H*W bytes per world-step).
-//   cw_step_kernel  one thread per world, K steps per launch, warp-cooperative auto-reset; compact observations.
-//                   Bound: latency / issue (tens of bytes per world-step).
-//   cw_onehot_kernel one-hot observation_vector expansion (12 bytes per cell).
+//   cw_env_kernel<V>   groups of worlds per CTA iteration: [step] -> [auto/forced Philox reset (+imagine_obs goal frame)]
+//                      -> render.  Grid tiles are staged in shared memory (cp.async), frames composed in a shared-memory
+//                      ring and streamed out with TMA bulk stores (cp.async.bulk shared::cta -> global): the global
+//                      write stream is full-line and issues no LSU store instructions.
+//                      Bound: HBM write bandwidth (48*H*W bytes per world-step).
+//                      V_PLAIN   ordinary launch (whole-grid dependency on the previous launch, PDL)
+//                      V_CHAINED consecutive step launches linked by per-group dataflow (cw_step_render_chained, 3.1b)
+//                      V_LIST    work-list launch: re-seed + render the worlds a preceding step launch queued (3.5)
+//   cw_step_kernel<E>  one thread per world, K steps per launch, warp-cooperative auto-reset; compact observations.
+//                      Bound: latency / issue (tens of bytes per world-step).  E = true: the thread also patches the
+//                      world's device frame (render_edit) and queues finished worlds instead of re-seeding them.
+//   cw_onehot_kernel, cw_render_alt_kernel   observation-format expanders: work items staged in shared memory at the
+//                      destination's 16-byte phase, TMA bulk stores, two stages (3.4).  Bound: HBM write.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>

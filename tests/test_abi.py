@@ -72,5 +72,17 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.cw_step(C.byref(cfg), C.byref(st), None, None, None, None, 7, None) == -3   # CW_E_BADFLAGS
     assert lib.cw_step(C.byref(cfg), C.byref(st), None, None, None, None, 1, None) == 0    # empty batch: no-op
     assert lib.cw_host_step(None, None, None, None, None) == -4                            # CW_E_BADHANDLE
+    # the newer step entry points validate the same way
+    st.n = 4
+    assert lib.cw_step_render_chained(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 0, None, 0, 1, None) == -2
+    assert lib.cw_step_render_edit(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 0, None, None) == -2
+    st.n = 0
+    assert lib.cw_step_render_chained(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 0, None, 1024, 1, None) == -1
+    assert lib.cw_step_render_chained(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 0, None, 0, 0, None) == -1
+    assert lib.cw_step_render_edit(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 2, None, None) == -3
+    assert lib.cw_step_delta(C.byref(cfg), C.byref(st), None, None, None, None, 0, 64, None) == 0   # empty batch wins over the tag check
+    tiny = make_config()
+    tiny.H = tiny.W = 1; tiny.cell_stride = 16
+    assert lib.cw_render(C.byref(tiny), None, None, None, 1, None) == -1                   # sides < 2 are rejected
     with pytest.raises(_lib.CwError):
         _lib.check(-1, "unit test")
