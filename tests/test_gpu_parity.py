@@ -442,15 +442,25 @@ def test_host_env_matches_oracle(cw):
     env.close()
 
 
-def test_no_out_of_bounds_writes_guard_bands(cw):
+@pytest.mark.parametrize("mode", ["full", "chained", "incremental"])
+def test_no_out_of_bounds_writes_guard_bands(cw, mode):
     """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with canaries: every buffer the
     kernels write is carved out of a larger allocation whose guard bands must stay untouched (odd sizes, auto-reset,
-    goal + init frames, multi-chunk frames at 64x64, tail groups)."""
+    goal + init frames, multi-chunk frames at 64x64, tail groups) -- for independent launches, chained launches and the
+    incremental (render_edit + work-list re-seed) path."""
     GUARD = 4096
     for size, N in ((21, 1031), (5, 77), (64, 37), (32, 300)):
-        env = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=9, seed=size)
+        env = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=9, seed=size,
+                                         render="incremental" if mode == "incremental" else "full")
+        if mode == "incremental":
+            env._edit_scratch = torch.zeros(N + 2, dtype=torch.int32, device="cuda")
+        if mode == "chained":
+            from gym_craftingworld_b200 import _lib as _l
+            env._chain = torch.zeros(_l.CHAIN_MAX_POS + N, dtype=torch.int32, device="cuda")
         pads = {}
-        for name in ("grid", "init_grid", "agent", "goal", "t", "episode", "reward", "_done_u8", "obs", "desired_goal", "init_obs"):
+        names = ["grid", "init_grid", "agent", "goal", "t", "episode", "reward", "_done_u8", "obs", "desired_goal", "init_obs"]
+        names += ["_edit_scratch"] if mode == "incremental" else (["_chain"] if mode == "chained" else [])
+        for name in names:
             old = getattr(env, name)
             nbytes = old.numel() * old.element_size()
             raw = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
@@ -464,7 +474,7 @@ def test_no_out_of_bounds_writes_guard_bands(cw):
         env.reset()
         acts = torch.randint(0, 6, (40, N), device="cuda", dtype=torch.uint8)
         for k in range(40):
-            env.step(acts[k])
+            env.step(acts[k], chain_pos=k if mode == "chained" else None)
         env.render()
         torch.cuda.synchronize()
         for name, raw in pads.items():
