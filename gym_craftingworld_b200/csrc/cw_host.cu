@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <sched.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -153,6 +154,9 @@ struct CwHostEnv {
     uint32_t seq;                     // sequence tag of the last delta step (1..63)
     const uint8_t* pinned_actions;    // last caller action buffer found to be page-locked
     bool nopatch;                     // CW_HOST_NOPATCH=1 (diagnostics only): consume the records, skip the frame patching
+    bool trace;                       // CW_HOST_TRACE=1 (diagnostics only): phase times of the delta step, printed at destroy
+    double tr_launch, tr_first, tr_total;   // accumulated microseconds: launch call, launch -> first record seen, whole call
+    uint64_t tr_steps;
 };
 
 #define CW_HOST_MAGIC 0x43574845u
@@ -236,6 +240,7 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
             e->pool = new (std::nothrow) WorkerPool(host_threads(n));
             if (!rc && e->h_delta) memset(e->h_delta, 0, n * sizeof(uint4));   // tag 0 = never written
             if (const char* np = getenv("CW_HOST_NOPATCH")) e->nopatch = *np == '1';
+            if (const char* tr = getenv("CW_HOST_TRACE")) e->trace = *tr == '1';
         }
     }
     TRY(cudaStreamCreateWithFlags(&e->streams[0], cudaStreamNonBlocking));
@@ -372,9 +377,16 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
             memcpy(pn + 2 * rowb + 3, hold ? kLut6[hold] : kWhite6, 6);   // ray.py:556-557
         }
     };
+    const auto t_begin = std::chrono::steady_clock::now();
     e->pool->start(job);                                          // workers poll while the launch is on its way
     int rc = cw_step_delta(&e->cfg, &e->st, act_src, e->h_delta, e->h_fresh, e->d_stats, e->flags & CW_F_AUTO_RESET, (int)seq, s);
     if (rc) failed.store(1);
+    const auto t_launched = std::chrono::steady_clock::now();
+    if (e->trace && !rc) {                                        // when does the first record of the caller's slice land?
+        const volatile uint32_t* tag = &reinterpret_cast<const volatile uint32_t*>(e->h_delta)[2];
+        while ((*tag >> 26) != seq && !failed.load(std::memory_order_relaxed)) cpu_relax();
+        e->tr_first += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launched).count();
+    }
     job(0, e->pool->size());
     // watchdog: once the launch has left the stream every record is in host memory; workers still polling 100 ms later
     // will never be served (a failed launch) -- release them instead of hanging the caller
@@ -385,6 +397,11 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
             if (!e->pool->done()) failed.store(1);
         }
         cpu_relax();
+    }
+    if (e->trace) {
+        e->tr_launch += std::chrono::duration<double, std::micro>(t_launched - t_begin).count();
+        e->tr_total += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
+        e->tr_steps++;
     }
     if (rc) return rc;
     if (failed.load()) {
@@ -466,6 +483,9 @@ int cw_host_device_state(CwHostEnv* e, CwState* out_state, uint8_t** out_obs) {
 int cw_host_destroy(CwHostEnv* e) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     cudaSetDevice(e->device);
+    if (e->trace && e->tr_steps)
+        fprintf(stderr, "cw_host trace: %llu delta steps; launch call %.2f us, launch -> first record %.2f us, whole call %.2f us\n",
+                (unsigned long long)e->tr_steps, e->tr_launch / e->tr_steps, e->tr_first / e->tr_steps, e->tr_total / e->tr_steps);
     if (e->streams[0]) cudaStreamSynchronize(e->streams[0]);     // the delta path returns without a stream sync
     if (e->streams[1]) cudaStreamSynchronize(e->streams[1]);
     cudaFree(e->st.grid); cudaFree(e->st.init_grid); cudaFree(e->st.agent); cudaFree(e->st.goal); cudaFree(e->st.t);
