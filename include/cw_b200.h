@@ -10,6 +10,10 @@
  *   - plain pointers and sizes only; every `uint8_t* / uint32_t* / int32_t* / int64_t*` below that is not marked
  *     "host" is a DEVICE pointer owned by the caller (PyTorch in our host layer); the library never allocates,
  *     frees or retains them (the cw_host_* family is the exception: it owns its own device + pinned buffers).
+ *   - alignment: grid / init_grid / goal_grid rows and every frame buffer (obs, goal_obs, init_obs) must start on a
+ *     16-byte boundary (tiles move as 16-byte chunks, frames leave through TMA bulk stores); word arrays on their natural
+ *     alignment.  cudaMalloc / PyTorch allocations satisfy this.  cw_onehot / cw_render_alt accept any 4- / 2-byte aligned
+ *     output (cw_onehot even an unaligned one, through a slower byte-wise path).
  *   - `stream` is a cudaStream_t passed as void*; all device entry points are asynchronous on it and never
  *     synchronise the host.
  *   - return value: 0 on success, a positive cudaError_t, or a negative CW_E_* argument error. Never throws.
