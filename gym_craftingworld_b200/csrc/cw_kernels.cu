@@ -105,8 +105,9 @@ enum : int { BAR_COMPOSE = 1, BAR_RESET_DONE = 2 };
 //      out with a TMA bulk store and only waits for the store issued F-1 slots earlier, so composing overlaps
 //      the stores.  Worlds the reset warp worked on are emitted last, after its named-barrier arrival.
 // dynamic shared memory: [tiles 2 x G x cell_stride][imagine scratch G x cell_stride][ring F x chunk_bytes]
-// kChained = false is the ordinary launch; true adds the chain protocol (a separate instantiation, so the ordinary
-// launch's code is exactly what it was -- the extra control flow measurably slowed it when it shared one body).
+// Three instantiations (V_PLAIN ordinary launch, V_CHAINED chain protocol, V_LIST work-list re-seed): separate code, so the
+// ordinary launch is exactly what it was -- the extra control flow measurably slowed it (6 % at 131072 worlds) when all
+// shared one kernel body.
 enum : int { V_PLAIN = 0, V_CHAINED = 1, V_LIST = 2 };
 template <int kVariant>
 __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
