@@ -524,6 +524,68 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
     CW_WSTAMP(4);
 }
 
+// Delta transport (cw_step_delta): one thread per world, records straight into (possibly host-mapped) memory.  The step of a
+// host-buffer call is a synchronous round trip, so what matters here is LATENCY to the records: no tile staging, no shared
+// memory, 32 CTAs at 4096 worlds; only the warps that hold a finished world pay for its re-seed (warp-cooperative Philox
+// reset + closed-form imagine_obs), every other record is on its way ~1 us after the actions arrive.
+__global__ void __launch_bounds__(128) cw_delta_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
+                                                       uint4* __restrict__ delta, uint32_t* __restrict__ fresh,
+                                                       unsigned long long* stats, uint32_t seq, int flags) {
+    __shared__ uint32_t s_obj[4][8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = n < st.n;
+    const int64_t nn = valid ? n : 0;
+    uint8_t* g = st.grid + nn * cfg.cell_stride;
+    uint32_t agent = 0, goal = 0, ep = 0, rew_u = 0;
+    int t = 0;
+    bool dn = false;
+    if (valid) {
+        const int a = actions[n];                                 // (host-mapped: the longest latency, issued first)
+        agent = __ldcg(st.agent + n); goal = __ldcg(st.goal + n); t = __ldcg(st.t + n);
+        ep = (flags & CW_F_AUTO_RESET) ? __ldcg(st.episode + n) : 0u;
+        int wcell, wval;
+        const int rew = step_core(cfg, g, st.init_grid + nn * cfg.cell_stride, agent, goal, t, a, dn, wcell, wval);
+        rew_u = (uint32_t)rew;
+        if (dn && (flags & CW_F_AUTO_RESET)) {
+            if (stats) stats_add(cfg, stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
+        } else {
+            st.agent[n] = agent; st.goal[n] = goal; st.t[n] = t;
+            delta[n] = make_uint4(agent, goal, (uint32_t)(wcell & 0xFFFF) | ((uint32_t)wval << 16) | (((dn ? 1u : 0u) | (seq << 2)) << 24), rew_u);
+        }
+    }
+    if (!(flags & CW_F_AUTO_RESET)) return;
+    uint32_t m = __ballot_sync(0xffffffffu, valid && dn);        // finished worlds of this warp, re-seeded by the whole warp
+    const int lane = lane_id();
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t env = __shfl_sync(0xffffffffu, n, src);
+        const uint32_t env_ep = __shfl_sync(0xffffffffu, ep, src), env_rew = __shfl_sync(0xffffffffu, rew_u, src);
+        WarpPhilox rng;
+        Sparse8 objs;
+        uint32_t ag, gl;
+        reset_warp(cfg, st, env, nullptr, rng, ag, gl, env_ep, &objs, s_obj[threadIdx.x >> 5]);   // ray.py:156-218
+        if (lane == 0) { st.agent[env] = ag; st.goal[env] = gl; st.t[env] = 0; if (st.init_agent) st.init_agent[env] = ag; }
+        uint32_t* fr = fresh + (size_t)env * CW_FRESH_WORDS;
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) word = lane == k ? (objs.cell[k] | (objs.code[k] << 16)) : word;
+        if (lane < 8) fr[lane] = word;
+        uint32_t gag = ag;
+        imagine_fresh(cfg, objs, gag, gl >> 16, rng);             // desired_goal = imagine_obs(): ray.py:191, 220-299
+        word = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) word = lane == k ? (objs.cell[k] | (objs.code[k] << 16)) : word;
+        if (lane < 8) fr[8 + lane] = word;
+        if (lane == 8) fr[16] = gag;
+        __threadfence_system();                                   // the 16-byte record goes last (see cw_env_kernel)
+        __syncwarp();
+        if (lane == 0) delta[env] = make_uint4(ag, gl, 0xFFFFu | ((3u /* done | fresh */ | (seq << 2)) << 24), env_rew);
+    }
+}
+
 // ---- observation-format expanders (one-hot state, AltObs frames): staged in shared memory, streamed out by TMA ------
 // Both outputs are contiguous over (world, ...), so a work item is a contiguous BYTE RANGE of the output: it is composed
 // in shared memory at the same address phase (mod 16) as its destination; the 16-byte aligned body leaves with ONE TMA
@@ -804,6 +866,7 @@ struct Tunables {
     int bands_per_chunk = env_int("CW_BANDS_PER_CHUNK", 0), chunk_bytes = env_int("CW_CHUNK_BYTES", 25 * 1024);
     int frame_buffers = env_int("CW_FRAME_BUFFERS", 0), first_split = env_int("CW_FIRST_SPLIT", 4);
     int ctas_per_sm = env_int("CW_CTAS_PER_SM", 0), group = env_int("CW_GROUP", 0);
+    int delta_env_kernel = env_int("CW_DELTA_ENV_KERNEL", 0);   // 1: cw_step_delta through the fused kernel (the older path)
 };
 static const Tunables& tunables() {
     static const Tunables t;
@@ -1042,6 +1105,12 @@ int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions
     if (st->n == 0) return 0;
     if (!actions || !delta || !fresh) return CW_E_NULLPTR;
     if (seq < 0 || seq > 63) return CW_E_BADCONFIG;
+    if (!st->goal_grid && tunables().delta_env_kernel == 0) {     // the latency path (the fused kernel remains for goal_grid users / A-B)
+        const int64_t blocks = (st->n + 127) / 128;
+        cudaError_t le = launch_pdl(cw_delta_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions,
+                                    (uint4*)delta, fresh, (unsigned long long*)stats, (uint32_t)seq, flags);
+        return (int)(le != cudaSuccess ? le : cudaGetLastError());
+    }
     EnvArgs a = {};
     a.delta_seq = (uint32_t)seq;
     a.actions = actions; a.delta = (uint4*)delta; a.fresh = fresh; a.stats = (unsigned long long*)stats;
