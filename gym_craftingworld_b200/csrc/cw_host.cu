@@ -318,18 +318,33 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
         const int64_t lo = n * tid / nt, hi = n * (tid + 1) / nt;
         uint8_t tmp[CW_MAX_SIDE * CW_MAX_SIDE];
         const size_t rowb = (size_t)12 * W;
-        for (int64_t w = lo; w < hi; w++) {
-            const volatile uint32_t* tag = &reinterpret_cast<const volatile uint32_t*>(e->h_delta + w)[2];
-            if ((*tag >> 26) != seq) {                            // not there yet: poll (the GPU's write invalidates the line)
-                uint64_t spins = 0;
-                while ((*tag >> 26) != seq) {
-                    if (failed.load(std::memory_order_relaxed)) return;
-                    if ((++spins & 0xFFFFF) == 0 && tid == 0 && cudaStreamQuery(s) != cudaErrorNotReady) {
-                        // the launch has finished (or failed): every record is in host memory now, or never will be
-                        if ((*tag >> 26) != seq) { failed.store(1); return; }
-                    }
-                    cpu_relax();
+        // Records do not arrive in order: a re-seeded world's record follows ~6 us after its neighbours' (its warp runs the
+        // Philox reset + imagine_obs first).  Worlds whose record is not there yet are deferred and revisited after the
+        // rest of the slice, so one late record does not stall the patching behind it.
+        constexpr int kMaxDeferred = 128;
+        int64_t deferred[kMaxDeferred];
+        int ndef = 0;
+        const int64_t total = hi - lo;
+        auto ready = [&](int64_t w) { return (reinterpret_cast<const volatile uint32_t*>(e->h_delta + w)[2] >> 26) == seq; };
+        auto wait_for = [&](int64_t w) {                          // poll (the GPU's write invalidates the line); false: launch failed
+            uint64_t spins = 0;
+            while (!ready(w)) {
+                if (failed.load(std::memory_order_relaxed)) return false;
+                if ((++spins & 0xFFFFF) == 0 && tid == 0 && cudaStreamQuery(s) != cudaErrorNotReady) {
+                    // the launch has finished (or failed): every record is in host memory now, or never will be
+                    if (!ready(w)) { failed.store(1); return false; }
                 }
+                cpu_relax();
+            }
+            return true;
+        };
+        if (total > 0 && !wait_for(lo)) return;                   // the step's records start to land
+        for (int64_t it = 0; it < total + ndef; it++) {
+            const bool second = it >= total;
+            const int64_t w = second ? deferred[it - total] : lo + it;
+            if (!ready(w)) {
+                if (!second && ndef < kMaxDeferred) { deferred[ndef++] = w; continue; }
+                if (!wait_for(w)) return;
             }
             std::atomic_thread_fence(std::memory_order_acquire);
             const uint4 r = e->h_delta[w];
