@@ -87,6 +87,9 @@ __device__ __forceinline__ uint32_t setbit(uint32_t m, int bit, bool on) {
     return on ? (m | (1u << bit)) : (m & ~(1u << bit));
 }
 
+// kEagerInit: read the two INIT_OBS cells unconditionally, together with the grid cells (one dependent load level less on
+// a latency-critical path), instead of only when something is held.
+template <bool kEagerInit = false>
 __device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restrict__ g, const uint8_t* __restrict__ ig,
                                          uint32_t& agent, uint32_t& goal, int& t, int a, bool& done, int& wcell,
                                          int& wval) {
@@ -116,7 +119,7 @@ __device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restric
         int here = g[cell];
         const int T = g[ncell];
         int ih = 0, ihn = 0;
-        if (h != 0) { ih = __ldcg(ig + cell); ihn = __ldcg(ig + ncell); }   // L2: a co-resident chained launch may have re-seeded it   // L2: a co-resident chained launch may have re-seeded it
+        if (kEagerInit || h != 0) { ih = __ldcg(ig + cell); ihn = __ldcg(ig + ncell); }   // L2: a co-resident chained launch may have re-seeded it   // L2: a co-resident chained launch may have re-seeded it
         int old = EMPTY;  // EMPTY == "None": matches no predicate below (ray.py:655 uses 100)
         bool moved = ncell != cell;                                              // ray.py:395-396
         const bool blocked = ((T == ROCK) & (h != HAMMER)) | ((T == TREE) & (h != AXE));   // ray.py:401-405

@@ -394,7 +394,8 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
     };
     const auto t_begin = std::chrono::steady_clock::now();
     e->pool->start(job);                                          // workers poll while the launch is on its way
-    int rc = cw_step_delta(&e->cfg, &e->st, act_src, e->h_delta, e->h_fresh, e->d_stats, e->flags & CW_F_AUTO_RESET, (int)seq, s);
+    int rc = cw_step_delta(&e->cfg, &e->st, act_src, e->h_delta, e->h_fresh, e->d_stats, (e->flags & CW_F_AUTO_RESET) | CW_F_HOST_ACTIONS,
+                           (int)seq, s);
     if (rc) failed.store(1);
     const auto t_launched = std::chrono::steady_clock::now();
     if (e->trace && !rc) {                                        // when does the first record of the caller's slice land?

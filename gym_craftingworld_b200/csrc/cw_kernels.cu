@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -528,9 +529,13 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
 // host-buffer call is a synchronous round trip, so what matters here is LATENCY to the records: no tile staging, no shared
 // memory, 32 CTAs at 4096 worlds; only the warps that hold a finished world pay for its re-seed (warp-cooperative Philox
 // reset + closed-form imagine_obs), every other record is on its way ~1 us after the actions arrive.
+constexpr int kParamActions = 4096;               // a batch up to this size can carry its actions in the kernel parameters
+struct ActionBlock { uint8_t a[kParamActions]; };
+template <bool kInParams>                         // kInParams: the actions arrive WITH the launch (no PCIe read of mapped host memory)
 __global__ void __launch_bounds__(128) cw_delta_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
-                                                       uint4* __restrict__ delta, uint32_t* __restrict__ fresh,
-                                                       unsigned long long* stats, uint32_t seq, int flags) {
+                                                       const __grid_constant__ ActionBlock pa, uint4* __restrict__ delta,
+                                                       uint32_t* __restrict__ fresh, unsigned long long* stats, uint32_t seq,
+                                                       int flags) {
     __shared__ uint32_t s_obj[4][8];
     pdl_launch_dependents();
     pdl_wait();
@@ -542,11 +547,11 @@ __global__ void __launch_bounds__(128) cw_delta_kernel(const CwConfig cfg, const
     int t = 0;
     bool dn = false;
     if (valid) {
-        const int a = actions[n];                                 // (host-mapped: the longest latency, issued first)
+        const int a = kInParams ? pa.a[n] : actions[n];           // (host-mapped memory: the longest latency, issued first)
         agent = __ldcg(st.agent + n); goal = __ldcg(st.goal + n); t = __ldcg(st.t + n);
         ep = (flags & CW_F_AUTO_RESET) ? __ldcg(st.episode + n) : 0u;
         int wcell, wval;
-        const int rew = step_core(cfg, g, st.init_grid + nn * cfg.cell_stride, agent, goal, t, a, dn, wcell, wval);
+        const int rew = step_core<true>(cfg, g, st.init_grid + nn * cfg.cell_stride, agent, goal, t, a, dn, wcell, wval);
         rew_u = (uint32_t)rew;
         if (dn && (flags & CW_F_AUTO_RESET)) {
             if (stats) stats_add(cfg, stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
@@ -1100,15 +1105,25 @@ int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions
                   int flags, int seq, void* stream) {
     int rc = check_config(cfg); if (rc) return rc;
     rc = check_state(st); if (rc) return rc;
-    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
+    if (flags & ~(CW_F_AUTO_RESET | CW_F_HOST_ACTIONS)) return CW_E_BADFLAGS;
     if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
     if (st->n == 0) return 0;
     if (!actions || !delta || !fresh) return CW_E_NULLPTR;
     if (seq < 0 || seq > 63) return CW_E_BADCONFIG;
     if (!st->goal_grid && tunables().delta_env_kernel == 0) {     // the latency path (the fused kernel remains for goal_grid users / A-B)
         const int64_t blocks = (st->n + 127) / 128;
-        cudaError_t le = launch_pdl(cw_delta_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions,
-                                    (uint4*)delta, fresh, (unsigned long long*)stats, (uint32_t)seq, flags);
+        const int kflags = flags & CW_F_AUTO_RESET;
+        cudaError_t le;
+        if ((flags & CW_F_HOST_ACTIONS) && st->n <= kParamActions) {   // small batch, actions readable here: ship them in the launch
+            static thread_local ActionBlock blk;
+            memcpy(blk.a, actions, (size_t)st->n);
+            le = launch_pdl(cw_delta_kernel<true>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions, blk,
+                            (uint4*)delta, fresh, (unsigned long long*)stats, (uint32_t)seq, kflags);
+        } else {
+            static const ActionBlock none = {};
+            le = launch_pdl(cw_delta_kernel<false>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions, none,
+                            (uint4*)delta, fresh, (unsigned long long*)stats, (uint32_t)seq, kflags);
+        }
         return (int)(le != cudaSuccess ? le : cudaGetLastError());
     }
     EnvArgs a = {};

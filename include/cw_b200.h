@@ -60,6 +60,9 @@ extern "C" {
 #define CW_F_AUTO_RESET 1 /* on done: add the episode to stats, Philox-reset the world in the same launch; the
                              returned reward/done are the finished episode's, state/obs the new episode's */
 #define CW_F_DEFER_RESET 8 /* internal (cw_step_render_edit): count and report a finished world but do not re-seed it in the step launch */
+#define CW_F_HOST_ACTIONS 16 /* cw_step_delta only: `actions` is ALSO readable by the calling CPU thread (mapped pinned host memory);
+                                for batches of <= 4096 worlds the library then ships the actions inside the kernel parameters, which
+                                saves the device a PCIe read on the latency-critical path */
 #define CW_F_DELTA_TRANSPORT 2 /* cw_host_create only: keep the caller's frame buffer current by delta records + host-side
                                   patching of the changed cells instead of copying every frame over PCIe */
 
