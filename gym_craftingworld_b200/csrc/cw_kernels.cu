@@ -630,30 +630,37 @@ __global__ void __launch_bounds__(kExpThreads) cw_onehot_kernel(const CwConfig c
     const int tid = threadIdx.x;
     const int64_t items = (n_cells + kOneHotCells - 1) / kOneHotCells;
     constexpr int kQuadIters = (kOneHotCells / 4 + kExpThreads - 1) / kExpThreads;   // 2
-    struct Loaded { uint32_t code[kQuadIters][4], ag[kQuadIters][2], cell0[kQuadIters]; };
-    auto load_item = [&](int64_t it, Loaded& L) {                // all loads of an item in flight together
+    struct Loaded { uint32_t code[kQuadIters][4], agA[kQuadIters], agB[kQuadIters], cell0[kQuadIters]; };
+    // (world, cell) of the first cell of this CTA's current item, advanced by a constant stride per iteration: the only
+    // 64-bit divisions of the kernel happen here, once
+    const int64_t c_first = (int64_t)blockIdx.x * kOneHotCells, c_stride = (int64_t)gridDim.x * kOneHotCells;
+    int64_t ld_env = c_first / HW;
+    uint32_t ld_rem = (uint32_t)(c_first - ld_env * HW);
+    const int64_t step_env = c_stride / HW;
+    const uint32_t step_rem = (uint32_t)(c_stride - step_env * HW);
+    const uint32_t wrap_off = (uint32_t)cfg.cell_stride - HW;    // byte offset correction for a cell that belongs to the next world
+    auto load_item = [&](int64_t it, Loaded& L) {                // all loads of an item in flight together; advances (ld_env, ld_rem)
         const int64_t c0 = it * kOneHotCells;
         const uint32_t cnt = (uint32_t)min((int64_t)kOneHotCells, n_cells - c0);
         const uint32_t nquad = (cnt + 3u) >> 2;
-        const int64_t env0 = c0 / HW;
-        const uint32_t rem0 = (uint32_t)(c0 - env0 * HW);
 #pragma unroll
         for (int u = 0; u < kQuadIters; u++) {
             const uint32_t q = tid + u * kExpThreads;
             const uint32_t j0 = q < nquad ? 4u * q : 0u;
-            const uint32_t idx = rem0 + j0;
+            const uint32_t idx = ld_rem + j0;
             const uint32_t de = __umulhi(idx, hw_magic);          // idx / HW  (idx < kOneHotCells + HW)
-            const int64_t env = env0 + de;
-            L.cell0[u] = idx - de * HW;
+            const int64_t env = ld_env + de;
+            const uint32_t c = idx - de * HW;
+            L.cell0[u] = c;
+            const uint8_t* gp = grid + env * cfg.cell_stride + c;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t ci = L.cell0[u] + i;
-                const bool wrap = ci >= HW;
-                L.code[u][i] = (j0 + i < cnt) ? grid[(env + (wrap ? 1 : 0)) * cfg.cell_stride + (wrap ? ci - HW : ci)] : 0u;
-            }
-            L.ag[u][0] = agent[env];
-            L.ag[u][1] = agent[env + 1 < n ? env + 1 : env];
+            for (int i = 0; i < 4; i++)
+                L.code[u][i] = (j0 + i < cnt) ? gp[i + ((c + i >= HW) ? wrap_off : 0u)] : 0u;
+            L.agA[u] = agent[env];
+            L.agB[u] = agent[env + 1 < n ? env + 1 : env];
         }
+        ld_env += step_env; ld_rem += step_rem;
+        if (ld_rem >= HW) { ld_rem -= HW; ld_env += 1; }
     };
     int stage = 0;
     Loaded cur, nxt;
@@ -672,22 +679,22 @@ __global__ void __launch_bounds__(kExpThreads) cw_onehot_kernel(const CwConfig c
         for (int u = 0; u < kQuadIters; u++) {
             const uint32_t q = tid + u * kExpThreads;
             if (q >= nquad) continue;
+            // agent words of the quad's world (A) and of the next world (B, for cells past the world boundary): position of
+            // the agent cell relative to the quad, and channels 8..11 (agent; holding sticks / axe / hammer) as one word
+            const uint32_t a = cur.agA[u], bb = cur.agB[u], c = cur.cell0[u];
+            const uint32_t ia = (a & 0xFF) * W + ((a >> 8) & 0xFF) - c;               // 0..3 if the agent of A is in the quad
+            const uint32_t ib = (bb & 0xFF) * W + ((bb >> 8) & 0xFF) + HW - c;        // same for B (cells c+i >= HW)
+            const uint32_t ha = (a >> 16) & 0xFF, hb = (bb >> 16) & 0xFF;
+            const uint32_t wa = 1u | ((ha >= 1 && ha <= 3) ? 1u << (8 * ha) : 0u), wb = 1u | ((hb >= 1 && hb <= 3) ? 1u << (8 * hb) : 0u);
+            const uint32_t nA = HW - c;                                               // cells i < nA belong to world A
             uint32_t w[12];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const uint32_t ci = cur.cell0[u] + i;
-                const bool wrap = ci >= HW;
-                const uint32_t cell = wrap ? ci - HW : ci, a = wrap ? cur.ag[u][1] : cur.ag[u][0], cd = cur.code[u][i];
-                const uint32_t acell = (a & 0xFF) * W + ((a >> 8) & 0xFF);
-                const uint32_t bit = 1u << (8 * ((cd - 1u) & 3u));
-                w[3 * i + 0] = (cd >= 1 && cd <= 4) ? bit : 0u;   // object channels 0..3
-                w[3 * i + 1] = (cd >= 5 && cd <= 8) ? bit : 0u;   // object channels 4..7
-                uint32_t w2 = 0;
-                if (cell == acell) {
-                    const uint32_t h = (a >> 16) & 0xFF;
-                    w2 = 1u | ((h >= 1 && h <= 3) ? 1u << (8 * h) : 0u);   // channel 8: agent; 9..11: holding
-                }
-                w[3 * i + 2] = w2;
+                const uint32_t cd = cur.code[u][i];
+                const unsigned long long m = (cd >= 1 && cd <= 8) ? 1ull << (8 * (cd - 1u)) : 0ull;   // object channels 0..7
+                w[3 * i + 0] = (uint32_t)m;
+                w[3 * i + 1] = (uint32_t)(m >> 32);
+                w[3 * i + 2] = ((uint32_t)i < nA) ? ((uint32_t)i == ia ? wa : 0u) : ((uint32_t)i == ib ? wb : 0u);
             }
             uint8_t* p = buf + 48u * q;
             if (phase == 0) {
