@@ -54,6 +54,14 @@ def test_unsupported_side_channels_are_explicit():
         cw.BatchedCraftingWorldEnv(4, store_gif=True)
     with pytest.raises(ValueError):
         cw.BatchedCraftingWorldEnv(4, obs_mode="ascii")
+    with pytest.raises(ValueError):
+        cw.BatchedCraftingWorldEnv(4, render="lazy")
+    with pytest.raises(ValueError):                                # incremental rendering patches ONE persistent pixel buffer
+        cw.BatchedCraftingWorldEnv(4, render="incremental", obs_mode="compact")
+    with pytest.raises(ValueError):
+        cw.BatchedCraftingWorldEnv(4, render="incremental", obs_buffers=2)
+    with pytest.raises(ValueError):
+        cw.HostCraftingWorldEnv(4, transport="carrier-pigeon")
 
 
 def test_product_never_imports_the_oracle():
