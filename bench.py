@@ -365,10 +365,11 @@ def run_ours(args):
             henv.close()
             barrier()
         e2e = dict(res["delta"])
-        e2e["api"] = ("HostCraftingWorldEnv(transport='delta').step -> cw_host_step: every step the actions are read from pinned "
-                      "host memory and reward, done AND the current pixel frames are in host memory when the call returns. The "
-                      "device writes a 16-byte delta record per world (72 B more for a re-seeded world) into mapped pinned memory; "
-                      "the library patches the <=3 changed cells of each world in the caller's pinned frame buffer (bit-identical "
+        e2e["api"] = ("HostCraftingWorldEnv(transport='delta').step -> cw_host_step: every step the actions come from host memory and "
+                      "reward, done AND the current pixel frames are in host memory when the call returns. A thread-per-world kernel "
+                      "writes a 16-byte sequence-tagged delta record per world (72 B more for a re-seeded world) into mapped pinned "
+                      "memory; the library's worker threads poll the records while the kernel runs (no stream sync) and patch the <=2 "
+                      "changed cells of each world in the caller's frame buffer -- what the reference's render_edit does (bit-identical "
                       "to a full device render + copy; tests/test_gpu_parity.py::test_host_env_delta_transport_matches_oracle)")
         e2e["frames_left_on_device"] = dict(res["device"], note="same call with obs_host=NULL: frames are rendered into HBM by the "
                                             "fused kernel for a device-side consumer; only reward/done return to the host")
@@ -402,7 +403,7 @@ def run_ours(args):
                                    "with a policy between the steps can use"} if ms_unchained else None),
             "incremental_render": incremental,
             "e2e": e2e or None,
-            "roofline": {"bound": "hbm", "kernel": "cw_env_kernel" if pixels else "cw_step_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": ("cw_env_kernel<V_CHAINED>" if chain else "cw_env_kernel<V_PLAIN>") if pixels else "cw_step_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "algorithmic_bytes_per_env_step": B, "units_per_launch": N, "launch_us": launch_s * 1e6,
                          "peak_source": peak_src,
