@@ -293,6 +293,30 @@ def run_ours(args):
         sampler.stop()                                           # the clock record covers warm-up + the timed region of `value`; the
                                                                  # nvidia-smi poller must not compete with the host threads of the e2e legs
 
+    # ---- compact workload: the same open-loop tape as ONE launch per 128 steps (cw_rollout) -------------------------
+    rollout = None
+    if not pixels:
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                env.rollout(tape, return_trace=False)
+            torch.cuda.synchronize()
+            barrier()
+            reps = max(1, min(K, 12800) // TAPE)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for _ in range(reps):
+                env.rollout(tape, return_trace=False)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            barrier()
+        rms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tmax = torch.tensor([rms], device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            rms = float(tmax.item())
+        rollout = {"value": N * world * reps * TAPE / (rms / 1e3), "unit": UNIT, "steps": reps * TAPE, "gpu_launches": reps,
+                   "note": f"cw_rollout: {TAPE} steps of the same tape per launch, state in registers across the steps (open loop only)"}
+
     # ---- the same workload with INCREMENTAL rendering (the reference's render_edit, cw_step_render_edit) --------------
     incremental = None
     if pixels and not args.no_incremental:
@@ -402,6 +426,7 @@ def run_ours(args):
                            "note": "the same K steps as independent (whole-grid dependent, PDL) launches: what a closed loop "
                                    "with a policy between the steps can use"} if ms_unchained else None),
             "incremental_render": incremental,
+            "rollout": rollout,
             "e2e": e2e or None,
             "roofline": {"bound": "hbm", "kernel": ("cw_env_kernel<V_CHAINED>" if chain else "cw_env_kernel<V_PLAIN>") if pixels else "cw_step_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
