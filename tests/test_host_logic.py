@@ -127,3 +127,15 @@ def test_bench_reference_arm_contract():
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_tools_and_entry_points_compile():
+    """bench.py, __graft_entry__.py and every probe under tools/ at least byte-compile (they only run on the GPU box)."""
+    import glob
+    import os
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(root, "tools", "*.py")))
+    assert len(files) >= 8
+    for f in files:
+        py_compile.compile(f, doraise=True)
