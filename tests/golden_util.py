@@ -9,9 +9,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_files():
-    """Step/render traces (the AltObs frame file has its own layout and loader)."""
+    """Step/render traces (the AltObs frame file and the OneHot / Flat variant runs have their own layouts and loaders)."""
     return sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("altobs"))
+                  if not os.path.basename(p).startswith(("altobs", "variants_")))
 
 
 def load_altobs(name="altobs_8x8.npz"):

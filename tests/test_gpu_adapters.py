@@ -125,6 +125,26 @@ def test_altobs_env_matches_reference_frames_and_oracle(cw):
     assert stacked.reset().shape == (4, 4, 21, 18, 3)
 
 
+@pytest.mark.parametrize("name", ["variants_onehot_6x6.npz", "variants_flat_8x8.npz"])
+def test_variant_envs_match_reference_runs(cw, name):
+    """The batched OneHot / Flat mirrors against runs frozen from the reference's own CraftingWorldEnvOneHot and
+    CraftingWorldEnvFlat classes (tests/golden/make_golden_variants.py): observation, reward, done at every step."""
+    import os
+    d = dict(np.load(os.path.join(gu.GOLDEN_DIR, name)))
+    size, max_steps, flat, B = int(d["size"]), int(d["max_steps"]), bool(d["flat"]), 3
+    cls = cw.BatchedCraftingWorldEnvFlat if flat else cw.BatchedCraftingWorldEnvOneHot
+    env = cls(B, size=(size, size), max_steps=max_steps, seed=0, auto_reset=False)
+    rep = lambda x: np.repeat(np.asarray(x)[None], B, axis=0)     # the same world B times
+    env.load_state(rep(d["grid0"]), rep(d["r0"]), rep(d["c0"]), rep(d["hold0"]), rep(d["desired"]))
+    first = env.obs if flat else env.observation["observation"]
+    assert np.array_equal(first.cpu().numpy(), rep(d["obs0"]))
+    for t, a in enumerate(d["actions"]):
+        obs, reward, done, _ = env.step(np.full(B, a, np.uint8))
+        got = obs if flat else obs["observation"]
+        assert np.array_equal(got.cpu().numpy(), rep(d["obs"][t])), t
+        assert reward.cpu().tolist() == [int(d["reward"][t])] * B and done.cpu().tolist() == [bool(d["done"][t])] * B, t
+
+
 def _random_compact_state(N, size, seed):
     """dense random worlds (p=0.5 per cell, uniform object type), random agent cell and held item"""
     rng = np.random.RandomState(seed)
