@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 STATS_LEN = 24
 STATS_REPLICAS = 16
 MAX_SIDE = 64
@@ -19,8 +19,9 @@ F_DELTA_TRANSPORT = 2
 
 # every symbol include/cw_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_step_render_chained", "cw_step_render_edit", "cw_step_delta", "cw_rollout",
-           "cw_imagine", "cw_onehot", "cw_render_alt", "cw_host_create", "cw_host_reset", "cw_host_step", "cw_host_stats",
-           "cw_host_device_state", "cw_host_destroy"]
+           "cw_imagine", "cw_onehot", "cw_render_alt", "cw_host_create", "cw_host_reset", "cw_host_bind_actions", "cw_host_step",
+           "cw_host_step_many", "cw_host_load_state", "cw_host_stats", "cw_host_device_state", "cw_host_stream", "cw_host_fetch_frames", "cw_host_sync",
+           "cw_host_destroy"]
 
 
 class CwConfig(C.Structure):
@@ -65,6 +66,12 @@ def _declare(lib):
         "cw_host_create": [cfgp, i64, ci, u64, u64, ci, C.POINTER(vp)],
         "cw_host_reset": [vp, vp, vp],
         "cw_host_step": [vp, vp, vp, vp, vp],
+        "cw_host_bind_actions": [vp, vp],
+        "cw_host_step_many": [vp, vp, ci, vp, vp, vp],
+        "cw_host_load_state": [vp, vp, vp, vp, vp, vp],
+        "cw_host_stream": [vp, C.POINTER(vp)],
+        "cw_host_sync": [vp],
+        "cw_host_fetch_frames": [vp, vp, vp],
         "cw_host_stats": [vp, vp],
         "cw_host_device_state": [vp, stp, C.POINTER(vp)],
         "cw_host_destroy": [vp],

@@ -89,10 +89,13 @@ __device__ __forceinline__ uint32_t setbit(uint32_t m, int bit, bool on) {
 
 // kEagerInit: read the two INIT_OBS cells unconditionally, together with the grid cells (one dependent load level less on
 // a latency-critical path), instead of only when something is held.
+// `ocode` / `ncode`: the object codes, AFTER the step, of the cell the agent stood on before the step and of the cell it stands
+// on now (the same cell unless it moved) -- everything a frame consumer needs to repaint the <= 2 cells a step touches
+// (render_edit, ray.py:522-557) without a copy of the grid.  Dead code for callers that ignore them.
 template <bool kEagerInit = false>
-__device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restrict__ g, const uint8_t* __restrict__ ig,
-                                         uint32_t& agent, uint32_t& goal, int& t, int a, bool& done, int& wcell,
-                                         int& wval) {
+__device__ __forceinline__ int step_core_ex(const CwConfig& cfg, uint8_t* __restrict__ g, const uint8_t* __restrict__ ig,
+                                            uint32_t& agent, uint32_t& goal, int& t, int a, bool& done, int& wcell,
+                                            int& wval, int& ocode, int& ncode) {
     const int W = cfg.W, H = cfg.H, M = cfg.max_steps;
     int r = agent & 0xFF, c = (agent >> 8) & 0xFF, h = (agent >> 16) & 0xFF;
     uint32_t ach = goal & 0xFFFFu;
@@ -112,14 +115,16 @@ __device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restric
         } else {
             changed = false;  // out-of-range action: defined no-op (reference: IndexError, ray.py:308)
         }
+        ocode = ncode = (wcell >= 0) ? wval : here;
     } else {                                                                     // move, ray.py:343-346, 380-440
         const int dr = (a == 2) - (a == 0), dc = (a == 1) - (a == 3);            // ray.py:130-131
         const int nr = min(max(r + dr, 0), H - 1), nc = min(max(c + dc, 0), W - 1);   // coordinates.py:22-25
         const int ncell = nr * W + nc;
         int here = g[cell];
+        ocode = here;                                                            // a move never changes the cell it leaves
         const int T = g[ncell];
         int ih = 0, ihn = 0;
-        if (kEagerInit || h != 0) { ih = __ldcg(ig + cell); ihn = __ldcg(ig + ncell); }   // L2: a co-resident chained launch may have re-seeded it   // L2: a co-resident chained launch may have re-seeded it
+        if (kEagerInit || h != 0) { ih = __ldcg(ig + cell); ihn = __ldcg(ig + ncell); }   // L2: a co-resident chained launch may have re-seeded it
         int old = EMPTY;  // EMPTY == "None": matches no predicate below (ray.py:655 uses 100)
         bool moved = ncell != cell;                                              // ray.py:395-396
         const bool blocked = ((T == ROCK) & (h != HAMMER)) | ((T == TREE) & (h != AXE));   // ray.py:401-405
@@ -135,6 +140,7 @@ __device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restric
             here = nv;
         }
         changed = moved;
+        ncode = here;
         // eval_task_edit: for EVERY move action, successful or not (ray.py:345-346, 646-703)
         if (old == BREAD) ach |= 1u << T_EAT_BREAD;                              // ray.py:657-659
         else if (old == ROCK) ach |= 1u << T_CHOP_ROCK;                          // ray.py:660-662
@@ -162,6 +168,14 @@ __device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restric
     agent = (uint32_t)r | ((uint32_t)c << 8) | ((uint32_t)h << 16);
     goal = ach | (des << 16);
     return reward;
+}
+
+template <bool kEagerInit = false>
+__device__ __forceinline__ int step_core(const CwConfig& cfg, uint8_t* __restrict__ g, const uint8_t* __restrict__ ig,
+                                         uint32_t& agent, uint32_t& goal, int& t, int a, bool& done, int& wcell,
+                                         int& wval) {
+    int ocode, ncode;
+    return step_core_ex<kEagerInit>(cfg, g, ig, agent, goal, t, a, done, wcell, wval, ocode, ncode);
 }
 
 // episode statistics of a finished episode (host reduces them across ranks with one small all-reduce)
@@ -573,7 +587,10 @@ __device__ __forceinline__ void tile_from_objects(const Sparse8& o, int nchunk, 
 // into the shared-memory frame chunk `frame` (uint32 words; a pixel row is 3*W words = 12 bytes per cell).
 // A thread owns one cell: colour LUT -> the three 32-bit words of its 4-pixel RGB span -> 4 pixel rows; the
 // owner of the agent cell patches rows 1,2 itself (2x2 white block :483, bottom row = held colour :484-486),
-// so no second pass / barrier is needed.  Lanes hit consecutive cells => word stride 3 => conflict-free STS.
+// so no second pass / barrier is needed.  Lanes hit consecutive cells => word stride 3, which is conflict-free only while a
+// warp stays inside one cell row: with W = 21 a warp straddles cell rows (a jump of 4 pixel rows = 9*W words) and ncu counts
+// ~49 % of the shared-store wavefronts as conflict replays (profiles/r1f_env_kernel_chained_cfg4_ncu_full.csv).  A
+// conflict-free one-band-per-warp mapping was measured slower: the kernel is bound by the HBM write stream.
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void compose_cell(const uint8_t* __restrict__ src, int i, int b, int col, int roww, int acell,
                                              uint32_t hc, uint32_t* __restrict__ frame, const uint32_t* __restrict__ slut) {

@@ -1,15 +1,23 @@
 // cw_host.cu -- host-buffer API: the batched env behind an opaque handle (cw_host_*, see include/cw_b200.h).
 //
-// Every argument is a HOST pointer.  One call = one reference-style `env.step(actions)` for N worlds:
-// actions go host->device, the fused step+reset+render launch runs in slices, reward/done (and the frames when
-// an obs buffer is passed) come back device->host.  Slices alternate between two streams so the D2H copy of
-// slice j overlaps the kernel of slice j+1; PCIe, not the kernel, bounds this path when frames are returned.
+// Every argument is a HOST pointer.  One call = one reference-style `env.step(actions)` for N worlds.  Three transports:
+//   device consumer (obs_host == NULL)   the fused step + reset + render kernel leaves the frames in HBM (a ring of two frame
+//       buffers); launches are chained by per-group dataflow, reward / done are written straight into mapped pinned host
+//       memory and the call returns when ONE mapped word says the step phase of every world is done -- no stream
+//       synchronisation, the frames of step k drain under step k+1.
+//   delta (CW_F_DELTA_TRANSPORT)         a thread-per-world kernel writes one pre-digested 16-byte record per world into
+//       mapped pinned memory; a small worker pool patches the <= 2 changed cells of each world in the caller's frame buffer
+//       while the kernel runs (the reference's render_edit, ray.py:522-557).  No stream synchronisation either.
+//   frames                               every rendered frame copied device -> host over PCIe (sliced, two streams).
 #include <cuda_runtime.h>
 #include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <atomic>
 #include <chrono>
@@ -21,6 +29,7 @@
 #include <vector>
 
 #include "cw_b200.h"
+#include "cw_internal.h"
 
 // ---- a small persistent worker pool for the host-side frame patching of the delta transport -----------------
 namespace {
@@ -84,48 +93,54 @@ private:
 constexpr uint8_t kLut[9][3] = {{0, 0, 0},   {110, 69, 39},  {255, 105, 180}, {100, 100, 200}, {100, 100, 100},
                             {0, 128, 0}, {205, 133, 63}, {197, 91, 97},   {240, 230, 140}};
 
-// the same colours repeated over 4 pixels (a full cell row) and over 2 pixels (an overlay row)
+// the same colours repeated over 4 pixels (a full cell row, padded to 16 bytes) and over 2 pixels (an overlay row, padded to
+// 8); index 9 = the agent's white.  Codes are 4-bit fields of a record: the tables cover all 16 values.
 struct LutRows {
-    uint8_t r12[9][12], r6[9][6];
+    uint8_t r12[16][16], r6[16][8];
     constexpr LutRows() : r12(), r6() {
-        for (int c = 0; c < 9; c++) {
-            for (int k = 0; k < 12; k++) r12[c][k] = kLut[c][k % 3];
-            for (int k = 0; k < 6; k++) r6[c][k] = kLut[c][k % 3];
+        for (int c = 0; c < 16; c++) {
+            for (int k = 0; k < 12; k++) r12[c][k] = c < 9 ? kLut[c][k % 3] : 255;
+            for (int k = 0; k < 6; k++) r6[c][k] = c < 9 ? kLut[c][k % 3] : 255;
         }
     }
 };
 constexpr LutRows kRows;
-constexpr auto& kLut12 = kRows.r12;
-constexpr auto& kLut6 = kRows.r6;
-const uint8_t kWhite6[6] = {255, 255, 255, 255, 255, 255};
+constexpr int kWhite = 9;
+
+inline void store6(uint8_t* p, int code) { memcpy(p, kRows.r6[code], 4); memcpy(p + 4, kRows.r6[code] + 4, 2); }
+inline void store12(uint8_t* p, int code) { memcpy(p, kRows.r12[code], 8); memcpy(p + 8, kRows.r12[code] + 8, 4); }
 
 // one cell of a host frame: 4x4 pixels of the object's colour, agent overlay on top (ray.py:550-557)
 inline void patch_cell(uint8_t* frame, int W, int cell, int code, bool agent_here, int hold) {
     const int r = cell / W, c = cell - r * W;
     const size_t rowb = (size_t)12 * W;
-    uint8_t px[12];
-    for (int k = 0; k < 4; k++) memcpy(px + 3 * k, kLut[code], 3);
     uint8_t* p = frame + (size_t)(4 * r) * rowb + 12 * c;
-    for (int y = 0; y < 4; y++) memcpy(p + y * rowb, px, 12);
+    for (int y = 0; y < 4; y++) store12(p + y * rowb, code);
     if (agent_here) {
-        memset(p + rowb + 3, 255, 6);                                     // ray.py:555
-        if (hold) { memcpy(p + 2 * rowb + 3, kLut[hold], 3); memcpy(p + 2 * rowb + 6, kLut[hold], 3); }   // ray.py:556-557
-        else memset(p + 2 * rowb + 3, 255, 6);
+        store6(p + rowb + 3, kWhite);                                    // ray.py:555
+        store6(p + 2 * rowb + 3, hold ? hold : kWhite);                  // ray.py:556-557
     }
 }
-// a whole host frame from a grid tile (ray.py:442-486): used for re-seeded worlds only
-inline void render_frame(uint8_t* frame, int H, int W, const uint8_t* g, uint32_t agent) {
-    const size_t rowb = (size_t)12 * W;
-    for (int br = 0; br < H; br++) {
-        uint8_t* row = frame + (size_t)(4 * br) * rowb;
-        for (int bc = 0; bc < W; bc++)
-            for (int k = 0; k < 4; k++) memcpy(row + 12 * bc + 3 * k, kLut[g[br * W + bc]], 3);
-        for (int k = 1; k < 4; k++) memcpy(row + k * rowb, row, rowb);
+// a whole host frame of a world that holds at most 8 objects (a re-seeded world or its imagined goal state, ray.py:442-486):
+// everything else is black, so the frame is one memset plus <= 9 cells
+inline void render_sparse(uint8_t* frame, int H, int W, const uint32_t* objs8, uint32_t agent) {
+    memset(frame, 0, (size_t)48 * H * W);
+    const int acell = (int)(agent & 0xFF) * W + (int)((agent >> 8) & 0xFF), hold = (int)((agent >> 16) & 0xFF);
+    int under = 0;
+    for (int k = 0; k < 8; k++) {
+        const int code = (int)(objs8[k] >> 16), cell = (int)(objs8[k] & 0xFFFFu);
+        if (!code) continue;
+        if (cell == acell) under = code;
+        else patch_cell(frame, W, cell, code, false, 0);
     }
-    const int ar = agent & 0xFF, ac = (agent >> 8) & 0xFF, h = (agent >> 16) & 0xFF;
-    patch_cell(frame, W, ar * W + ac, g[ar * W + ac], true, h);
+    patch_cell(frame, W, acell, under, true, hold);
 }
 }  // namespace
+
+struct Bound {                          // a caller buffer declared with cw_host_bind: host address + its device alias when page-locked
+    void* host = nullptr;
+    void* dev = nullptr;                // non-null: mapped pinned memory, the device reads / writes it directly
+};
 
 struct CwHostEnv {
     uint32_t magic;
@@ -133,29 +148,34 @@ struct CwHostEnv {
     CwState st;
     int device, flags;
     size_t frame_bytes;
-    uint8_t *d_actions, *d_done, *d_obs, *d_goal_obs;
+    uint8_t *d_actions, *d_done, *d_obs[4], *d_goal_obs;
+    int nring;                        // frame buffers of the device-consumer transport (2..4; CW_HOST_RING)
     int32_t* d_reward;
     int64_t* d_stats;
-    uint8_t *h_actions, *h_done;      // pinned staging for the small vectors
+    uint8_t *h_actions, *h_done;      // pinned (mapped) staging for the small vectors
     int32_t* h_reward;
     int64_t* h_stats;
     uint8_t* h_frames;                // pinned staging for frames when the caller's buffer is pageable
     size_t h_frames_bytes;
     cudaStream_t streams[2];
-    int64_t slice;                    // worlds per slice
+    int64_t slice;                    // worlds per slice (frames transport)
+    int cur;                          // frame buffer holding the current observation (device consumer: alternates)
+    Bound b_actions;                  // cw_host_bind_actions
+    // device-consumer transport: chained launches + one self-validating status byte per world and step
+    uint32_t* d_chain;                // [CW_CHAIN_MAX_POS + N] chain words of cw_step_render_chained
+    uint8_t* h_status;                // pinned + mapped: [K][status_stride] status bytes (grown on demand), then [K][N] staged actions
+    size_t h_status_bytes;
+    int chain_pos;                    // position of the next launch in the open chain (0: the next launch opens one)
     // delta transport (CW_F_DELTA_TRANSPORT)
     uint4* h_delta;                   // pinned + mapped: per-world delta records written by the kernel
     uint32_t* h_fresh;                // pinned + mapped: sparse records of re-seeded worlds
-    uint8_t* m_grid;                  // host mirror of the grids (the state the caller's frames show)
-    uint32_t* m_agent;                // host mirror of the agent words
-    uint8_t* mirror_obs;              // caller buffers the mirror currently describes
+    uint8_t* mirror_obs;              // caller buffers the delta records currently describe (nullptr: unknown -> refresh)
     uint8_t* mirror_goal;
     WorkerPool* pool;
     uint32_t seq;                     // sequence tag of the last delta step (1..63)
-    const uint8_t* pinned_actions;    // last caller action buffer found to be page-locked
     bool nopatch;                     // CW_HOST_NOPATCH=1 (diagnostics only): consume the records, skip the frame patching
-    bool trace;                       // CW_HOST_TRACE=1 (diagnostics only): phase times of the delta step, printed at destroy
-    double tr_launch, tr_first, tr_total;   // accumulated microseconds: launch call, launch -> first record seen, whole call
+    bool trace;                       // CW_HOST_TRACE=1 (diagnostics only): phase times, printed at destroy
+    double tr_launch, tr_first, tr_total, tr_first_byte;   // accumulated microseconds: launch call, launch -> first record / flag seen, whole call
     uint64_t tr_steps;
 };
 
@@ -179,10 +199,11 @@ static int host_threads(int64_t n) {
     return nt < 1 ? 1 : nt;
 }
 
-static bool is_pinned(const void* p) {
+// device alias of a page-locked host buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory), nullptr for pageable memory
+static void* device_alias(const void* p) {
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 static CwState slice_state(const CwHostEnv* e, int64_t off, int64_t cnt) {
@@ -193,13 +214,66 @@ static CwState slice_state(const CwHostEnv* e, int64_t off, int64_t cnt) {
     return s;
 }
 
-static int ensure_frame_staging(CwHostEnv* e) {
-    const size_t need = (size_t)e->st.n * e->frame_bytes;
-    if (e->h_frames_bytes >= need) return 0;
-    if (e->h_frames) cudaFreeHost(e->h_frames);
-    e->h_frames = nullptr; e->h_frames_bytes = 0;
-    CK(cudaMallocHost(&e->h_frames, need));
-    e->h_frames_bytes = need;
+static int ensure_pinned(uint8_t** buf, size_t* have, size_t need) {
+    if (*have >= need) return 0;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr; *have = 0;
+    CK(cudaMallocHost(buf, need));
+    *have = need;
+    return 0;
+}
+static int ensure_frame_staging(CwHostEnv* e) { return ensure_pinned(&e->h_frames, &e->h_frames_bytes, (size_t)e->st.n * e->frame_bytes); }
+
+// Wait for the status bytes of one step (uint8[n] in mapped pinned memory, zero before the launch; the kernel stores
+// 0x80 | success << 1 | done per world) and unpack them into the caller's reward / done arrays.  A watchdog on the stream
+// turns a failed launch into an error instead of a hang.
+static int collect_status(const uint8_t* status, int64_t n, int32_t max_steps, int32_t* reward, uint8_t* done, cudaStream_t s,
+                          double* t_first_us = nullptr) {
+    uint64_t spins = 0;
+    if (t_first_us) {                                             // (CW_HOST_TRACE) when does the first byte land?
+        const auto t0 = std::chrono::steady_clock::now();
+        while (!(*reinterpret_cast<const volatile uint8_t*>(status) & 0x80u) && spins++ < (1ull << 26)) cpu_relax();
+        *t_first_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        spins = 0;
+    }
+    auto stalled = [&]() -> int {                                 // 0: keep polling
+        cpu_relax();
+        if ((++spins & 0xFFFF) != 0) return 0;
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q == cudaErrorNotReady) return 0;
+        return (int)(q != cudaSuccess ? q : cudaErrorLaunchFailure);   // the stream drained and the byte never came
+    };
+    int64_t w = 0;
+#if defined(__SSE2__)
+    const __m128i one = _mm_set1_epi8(1), two = _mm_set1_epi8(2), zero = _mm_setzero_si128();
+    const __m128i hit = _mm_set1_epi32(max_steps + 1), minus1 = _mm_set1_epi32(-1);
+    for (; w + 16 <= n; w += 16) {
+        __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(status + w));
+        int drained = 0;
+        while (_mm_movemask_epi8(v) != 0xFFFF) {                  // bit 7 of every byte = "written"
+            if (drained) return drained;                          // (one last look after the stream drained)
+            drained = stalled();
+            asm volatile("" ::: "memory");
+            v = _mm_load_si128(reinterpret_cast<const __m128i*>(status + w));
+        }
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(done + w), _mm_and_si128(v, one));
+        const __m128i succ = _mm_cmpeq_epi8(_mm_and_si128(v, two), two);   // 0xFF where reward == max_steps
+        const __m128i lo = _mm_unpacklo_epi8(succ, succ), hi = _mm_unpackhi_epi8(succ, succ);
+        const __m128i m[4] = {_mm_unpacklo_epi16(lo, lo), _mm_unpackhi_epi16(lo, lo), _mm_unpacklo_epi16(hi, hi), _mm_unpackhi_epi16(hi, hi)};
+        for (int q = 0; q < 4; q++)                               // -1 + (max_steps + 1) where successful
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(reward + w + 4 * q), _mm_add_epi32(minus1, _mm_and_si128(m[q], hit)));
+        (void)zero;
+    }
+#endif
+    for (; w < n; w++) {
+        const volatile uint8_t* p = status + w;
+        int drained = 0;
+        while (!(*p & 0x80u)) { if (drained) return drained; drained = stalled(); }
+        const uint8_t b = *p;
+        done[w] = b & 1u;
+        reward[w] = (b & 2u) ? max_steps : -1;
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     return 0;
 }
 
@@ -212,11 +286,11 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
     CK(cudaSetDevice(device));
     CwHostEnv* e = new (std::nothrow) CwHostEnv();
     if (!e) return (int)cudaErrorMemoryAllocation;
-    memset(e, 0, sizeof(*e));
     e->magic = CW_HOST_MAGIC; e->cfg = *cfg; e->device = device; e->flags = flags;
     e->frame_bytes = (size_t)48 * cfg->H * cfg->W;
     e->st.n = n; e->st.seed = seed; e->st.env_id_base = env_id_base;
     const size_t gb = (size_t)n * cfg->cell_stride;
+    const size_t chain_words = (size_t)CW_CHAIN_MAX_POS + (size_t)n;
     int rc = 0;
 #define TRY(x) do { if (!rc) { cudaError_t e_ = (x); if (e_ != cudaSuccess) rc = (int)e_; } } while (0)
     TRY(cudaMalloc(&e->st.grid, gb)); TRY(cudaMalloc(&e->st.init_grid, gb));
@@ -225,8 +299,17 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
     TRY(cudaMalloc(&e->d_actions, n));
     TRY(cudaMalloc(&e->d_reward, n * 5));                       // [reward int32 x n][done uint8 x n], one block
     if (!rc) e->d_done = reinterpret_cast<uint8_t*>(e->d_reward) + n * 4;
-    TRY(cudaMalloc(&e->d_obs, (size_t)n * e->frame_bytes)); TRY(cudaMalloc(&e->d_goal_obs, (size_t)n * e->frame_bytes));
+    TRY(cudaMalloc(&e->d_obs[0], (size_t)n * e->frame_bytes)); TRY(cudaMalloc(&e->d_goal_obs, (size_t)n * e->frame_bytes));
+    e->nring = 1;
+    if (!(flags & CW_F_DELTA_TRANSPORT)) {                        // (a delta handle renders on the device only to refresh)
+        // chained launches overlap step k+1 with the draining stores of step k: that needs >= 2 frame buffers, and a launch may
+        // not store before the launch `nring` positions back has completed -- small batches get more slack
+        e->nring = (size_t)n * e->frame_bytes * 4 <= ((size_t)1 << 30) ? 4 : 2;
+        if (const char* r = getenv("CW_HOST_RING")) { const int v = atoi(r); if (v >= 2 && v <= 4) e->nring = v; }
+        for (int i = 1; i < e->nring; i++) TRY(cudaMalloc(&e->d_obs[i], (size_t)n * e->frame_bytes));
+    }
     TRY(cudaMalloc(&e->d_stats, CW_STATS_REPLICAS * CW_STATS_LEN * 8));
+    TRY(cudaMalloc(&e->d_chain, chain_words * 4));
     TRY(cudaMallocHost(&e->h_actions, n)); TRY(cudaMallocHost(&e->h_reward, n * 5));
     if (!rc) e->h_done = reinterpret_cast<uint8_t*>(e->h_reward) + n * 4;
     TRY(cudaMallocHost(&e->h_stats, CW_STATS_REPLICAS * CW_STATS_LEN * 8));
@@ -234,15 +317,13 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
         TRY(cudaMallocHost(&e->h_delta, n * sizeof(uint4)));
         TRY(cudaMallocHost(&e->h_fresh, n * CW_FRESH_WORDS * sizeof(uint32_t)));
         if (!rc) {
-            e->m_grid = (uint8_t*)malloc(gb);
-            e->m_agent = (uint32_t*)malloc(n * 4);
-            if (!e->m_grid || !e->m_agent) rc = (int)cudaErrorMemoryAllocation;
             e->pool = new (std::nothrow) WorkerPool(host_threads(n));
-            if (!rc && e->h_delta) memset(e->h_delta, 0, n * sizeof(uint4));   // tag 0 = never written
-            if (const char* np = getenv("CW_HOST_NOPATCH")) e->nopatch = *np == '1';
-            if (const char* tr = getenv("CW_HOST_TRACE")) e->trace = *tr == '1';
+            if (!e->pool) rc = (int)cudaErrorMemoryAllocation;
+            if (e->h_delta) memset(e->h_delta, 0, n * sizeof(uint4));   // tag 0 = never written
         }
     }
+    if (const char* np = getenv("CW_HOST_NOPATCH")) e->nopatch = *np == '1';
+    if (const char* tr = getenv("CW_HOST_TRACE")) e->trace = *tr == '1';
     TRY(cudaStreamCreateWithFlags(&e->streams[0], cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&e->streams[1], cudaStreamNonBlocking));
     if (!rc) {
@@ -250,6 +331,7 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
         TRY(cudaMemset(e->st.agent, 0, n * 4)); TRY(cudaMemset(e->st.goal, 0, n * 4));
         TRY(cudaMemset(e->st.t, 0, n * 4)); TRY(cudaMemset(e->st.episode, 0, n * 4));
         TRY(cudaMemset(e->d_stats, 0, CW_STATS_REPLICAS * CW_STATS_LEN * 8));
+        TRY(cudaMemset(e->d_chain, 0, chain_words * 4));
         TRY(cudaDeviceSynchronize());
     }
 #undef TRY
@@ -262,32 +344,58 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
     return 0;
 }
 
+int cw_host_bind_actions(CwHostEnv* e, const uint8_t* actions_host) {
+    if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
+    CK(cudaSetDevice(e->device));
+    e->b_actions.host = (void*)actions_host; e->b_actions.dev = device_alias(actions_host);
+    return 0;
+}
+
+int cw_host_sync(CwHostEnv* e) {
+    if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->streams[0]));
+    CK(cudaStreamSynchronize(e->streams[1]));
+    return 0;
+}
+
 int cw_host_reset(CwHostEnv* e, uint8_t* obs_host, uint8_t* goal_obs_host) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     CK(cudaSetDevice(e->device));
     cudaStream_t s = e->streams[0];
-    int rc = cw_reset(&e->cfg, &e->st, nullptr, e->d_obs, e->d_goal_obs, nullptr, s);
+    e->chain_pos = 0; e->cur = 0;
+    int rc = cw_reset(&e->cfg, &e->st, nullptr, e->d_obs[0], e->d_goal_obs, nullptr, s);
     if (rc) return rc;
     const size_t total = (size_t)e->st.n * e->frame_bytes;
-    for (int which = 0; which < 2; which++) {
-        uint8_t* dst = which ? goal_obs_host : obs_host;
-        const uint8_t* src = which ? e->d_goal_obs : e->d_obs;
-        if (!dst) continue;
-        if (is_pinned(dst)) { CK(cudaMemcpyAsync(dst, src, total, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
-        else {
-            rc = ensure_frame_staging(e); if (rc) return rc;
-            CK(cudaMemcpyAsync(e->h_frames, src, total, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            memcpy(dst, e->h_frames, total);
-        }
-    }
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, e->d_obs[0], total, cudaMemcpyDeviceToHost, s));       // (pageable targets are staged by the runtime)
+    if (goal_obs_host) CK(cudaMemcpyAsync(goal_obs_host, e->d_goal_obs, total, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (e->flags & CW_F_DELTA_TRANSPORT) {                       // (re)build the host mirror
-        CK(cudaMemcpy(e->m_grid, e->st.grid, (size_t)e->st.n * e->cfg.cell_stride, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(e->m_agent, e->st.agent, (size_t)e->st.n * 4, cudaMemcpyDeviceToHost));
-        e->mirror_obs = obs_host;
-        e->mirror_goal = goal_obs_host;
+    e->mirror_obs = (e->flags & CW_F_DELTA_TRANSPORT) ? obs_host : nullptr;
+    e->mirror_goal = (e->flags & CW_F_DELTA_TRANSPORT) ? goal_obs_host : nullptr;
+    return 0;
+}
+
+int cw_host_load_state(CwHostEnv* e, const uint8_t* grid_host, const uint32_t* agent_host, const uint32_t* goal_host,
+                       const int32_t* t_host, uint8_t* obs_host) {
+    if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->streams[0])); CK(cudaStreamSynchronize(e->streams[1]));
+    const int64_t n = e->st.n;
+    const size_t gb = (size_t)n * e->cfg.cell_stride;
+    if (grid_host) {                                              // INIT_OBS_VECTOR := the injected state (ray.py:183)
+        CK(cudaMemcpy(e->st.grid, grid_host, gb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(e->st.init_grid, grid_host, gb, cudaMemcpyHostToDevice));
     }
+    if (agent_host) CK(cudaMemcpy(e->st.agent, agent_host, n * 4, cudaMemcpyHostToDevice));
+    if (goal_host) CK(cudaMemcpy(e->st.goal, goal_host, n * 4, cudaMemcpyHostToDevice));
+    if (t_host) CK(cudaMemcpy(e->st.t, t_host, n * 4, cudaMemcpyHostToDevice));
+    e->chain_pos = 0; e->cur = 0;
+    e->mirror_obs = nullptr;                                      // the caller's frames no longer describe the device state
+    int rc = cw_render(&e->cfg, e->st.grid, e->st.agent, e->d_obs[0], n, e->streams[0]);
+    if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, e->d_obs[0], (size_t)n * e->frame_bytes, cudaMemcpyDeviceToHost, e->streams[0]));
+    CK(cudaStreamSynchronize(e->streams[0]));
+    if (obs_host && (e->flags & CW_F_DELTA_TRANSPORT)) e->mirror_obs = obs_host;
     return 0;
 }
 
@@ -295,18 +403,20 @@ int cw_host_reset(CwHostEnv* e, uint8_t* obs_host, uint8_t* goal_obs_host) {
 // kernel runs.  There is no stream synchronisation on this path: every record carries the step's 6-bit sequence tag
 // (one 16-byte store, preceded system-wide by the sparse record of a re-seeded world), the workers are started before
 // the launch and poll the records of their slice; when every record of the step has been consumed the step is complete.
+// A record is pre-digested by the device -- where the agent stood, where it stands, the object codes of both cells after the
+// step, whether the object under the agent changed -- so the host keeps no copy of the grid and the patch loop has no
+// dependent loads: it prefetches the <= 4 destination lines of a world a few worlds ahead and then only stores.
 static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward_host, uint8_t* done_host, uint8_t* obs_host) {
     cudaStream_t s = e->streams[0];
     const int64_t n = e->st.n;
-    const int H = e->cfg.H, W = e->cfg.W, cs = e->cfg.cell_stride;
+    const int H = e->cfg.H, W = e->cfg.W;
+    e->chain_pos = 0;
     if (obs_host != e->mirror_obs) {                              // unknown buffer: one full refresh, then deltas
-        int rc = cw_render(&e->cfg, e->st.grid, e->st.agent, e->d_obs, n, s);
+        int rc = cw_render(&e->cfg, e->st.grid, e->st.agent, e->d_obs[0], n, s);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(obs_host, e->d_obs, (size_t)n * e->frame_bytes, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(e->m_grid, e->st.grid, (size_t)n * cs, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(e->m_agent, e->st.agent, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(obs_host, e->d_obs[0], (size_t)n * e->frame_bytes, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        e->mirror_obs = obs_host;
+        e->mirror_obs = obs_host; e->cur = 0;
     }
     e->seq = e->seq >= 63 ? 1 : e->seq + 1;                       // 1..63; 0 is the never-written state of the buffer
     const uint32_t seq = e->seq;
@@ -314,18 +424,20 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
     uint8_t* goal = e->mirror_goal;
     std::atomic<int> failed{0};
     const bool nopatch = e->nopatch;
-    const std::function<void(int, int)> job = [&, n, H, W, cs, seq, fb, goal, nopatch](int tid, int nt) {
+    const uint4* recs = e->h_delta;
+    const uint32_t* fresh = e->h_fresh;
+    const std::function<void(int, int)> job = [&, n, H, W, seq, fb, goal, nopatch, recs, fresh](int tid, int nt) {
         const int64_t lo = n * tid / nt, hi = n * (tid + 1) / nt;
-        uint8_t tmp[CW_MAX_SIDE * CW_MAX_SIDE];
         const size_t rowb = (size_t)12 * W;
         // Records do not arrive in order: a re-seeded world's record follows ~6 us after its neighbours' (its warp runs the
         // Philox reset + imagine_obs first).  Worlds whose record is not there yet are deferred and revisited after the
         // rest of the slice, so one late record does not stall the patching behind it.
-        constexpr int kMaxDeferred = 128;
+        constexpr int kMaxDeferred = 128, kAhead = 8;
         int64_t deferred[kMaxDeferred];
         int ndef = 0;
         const int64_t total = hi - lo;
-        auto ready = [&](int64_t w) { return (reinterpret_cast<const volatile uint32_t*>(e->h_delta + w)[2] >> 26) == seq; };
+        auto word = [&](int64_t w, int i) { return reinterpret_cast<const volatile uint32_t*>(recs + w)[i]; };
+        auto ready = [&](int64_t w) { return (word(w, 2) >> 26) == seq; };
         auto wait_for = [&](int64_t w) {                          // poll (the GPU's write invalidates the line); false: launch failed
             uint64_t spins = 0;
             while (!ready(w)) {
@@ -338,58 +450,55 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
             }
             return true;
         };
+        auto prefetch = [&](int64_t w) {                          // the overlay rows of the cell left and of the cell entered
+            const uint32_t x = word(w, 0), z = word(w, 2);
+            if ((z >> 26) != seq || ((z >> 24) & 2u)) return;
+            uint8_t* frame = obs_host + w * fb;
+            const uint8_t* po = frame + (size_t)(4 * (z & 63u) + 1) * rowb + 12 * ((z >> 6) & 63u) + 3;
+            const uint8_t* pn = frame + (size_t)(4 * (x & 0xFFu) + 1) * rowb + 12 * ((x >> 8) & 0xFFu) + 3;
+            __builtin_prefetch(po, 1); __builtin_prefetch(po + rowb, 1);
+            __builtin_prefetch(pn, 1); __builtin_prefetch(pn + rowb, 1);
+        };
         if (total > 0 && !wait_for(lo)) return;                   // the step's records start to land
+        if (!nopatch) for (int64_t w = lo; w < lo + kAhead && w < hi; w++) prefetch(w);
         for (int64_t it = 0; it < total + ndef; it++) {
             const bool second = it >= total;
             const int64_t w = second ? deferred[it - total] : lo + it;
+            if (!second && !nopatch && w + kAhead < hi) prefetch(w + kAhead);
             if (!ready(w)) {
                 if (!second && ndef < kMaxDeferred) { deferred[ndef++] = w; continue; }
                 if (!wait_for(w)) return;
             }
             std::atomic_thread_fence(std::memory_order_acquire);
-            const uint4 r = e->h_delta[w];
+            const uint4 r = recs[w];
             const uint32_t flags = r.z >> 24;
             reward_host[w] = (int32_t)r.w;
             done_host[w] = (uint8_t)(flags & 1u);
             if (nopatch) continue;
-            uint8_t* g = e->m_grid + w * cs;
             uint8_t* frame = obs_host + w * fb;
-            if (flags & 2u) {                                     // re-seeded: rebuild tile + frame (+ goal frame)
-                const uint32_t* fr = e->h_fresh + w * CW_FRESH_WORDS;
-                memset(g, 0, cs);
-                for (int k = 0; k < 8; k++) if (fr[k] >> 16) g[fr[k] & 0xFFFFu] = (uint8_t)(fr[k] >> 16);
-                e->m_agent[w] = r.x;
-                render_frame(frame, H, W, g, r.x);
-                if (goal) {
-                    memset(tmp, 0, (size_t)H * W);
-                    for (int k = 8; k < 16; k++) if (fr[k] >> 16) tmp[fr[k] & 0xFFFFu] = (uint8_t)(fr[k] >> 16);
-                    render_frame(goal + w * fb, H, W, tmp, fr[16]);
-                }
+            if (flags & 2u) {                                     // re-seeded: the new world (+ its goal frame) from the sparse record
+                const uint32_t* fr = fresh + w * CW_FRESH_WORDS;
+                render_sparse(frame, H, W, fr, r.x);
+                if (goal) render_sparse(goal + w * fb, H, W, fr + 8, fr[16]);
                 continue;
             }
             // render_edit (ray.py:522-557) on the <= 2 cells a step can change.  A cell whose OBJECT is unchanged differs
             // only in the centred 2x2 overlay block, so it costs two 6-byte writes instead of four 12-byte rows.
-            const uint32_t old = e->m_agent[w];
-            const int wcell = (int)(r.z & 0xFFFFu);
-            if (wcell != 0xFFFF) g[wcell] = (uint8_t)((r.z >> 16) & 0xFFu);
-            else if (old == r.x) continue;                        // nothing visible changed
-            e->m_agent[w] = r.x;
-            const int orow = (int)(old & 0xFF), ocol = (int)((old >> 8) & 0xFF);
+            const uint32_t z = r.z;
+            const int orow = (int)(z & 63u), ocol = (int)((z >> 6) & 63u), ocode = (int)((z >> 12) & 15u), ncode = (int)((z >> 16) & 15u);
             const int nrow = (int)(r.x & 0xFF), ncol = (int)((r.x >> 8) & 0xFF), hold = (int)((r.x >> 16) & 0xFF);
-            const int oc = orow * W + ocol, nc = nrow * W + ncol;
-            uint8_t* po = frame + (size_t)(4 * orow) * rowb + 12 * ocol;
+            const bool objchg = (z >> 20) & 1u, moved = (orow != nrow) | (ocol != ncol);
+            if (!moved && !objchg) continue;                      // nothing visible changed
             uint8_t* pn = frame + (size_t)(4 * nrow) * rowb + 12 * ncol;
-            if (oc != nc) {                                       // the agent left `oc`; its object did not change
-                const uint8_t* col = kLut6[g[oc]];
-                memcpy(po + rowb + 3, col, 6); memcpy(po + 2 * rowb + 3, col, 6);
+            if (moved) {                                          // the agent left a cell whose object did not change
+                uint8_t* po = frame + (size_t)(4 * orow + 1) * rowb + 12 * ocol + 3;
+                store6(po, ocode); store6(po + rowb, ocode);
             }
-            if (wcell != 0xFFFF && wcell != nc) patch_cell(frame, W, wcell, g[wcell], false, 0);   // (not produced by step())
-            if (wcell == nc) {                                    // the object under the agent changed: all four rows
-                const uint8_t* col = kLut12[g[nc]];
-                for (int y = 0; y < 4; y++) memcpy(pn + y * rowb, col, 12);
+            if (objchg) {                                         // the object under the agent changed: all four rows
+                for (int y = 0; y < 4; y++) store12(pn + y * rowb, ncode);
             }
-            memset(pn + rowb + 3, 255, 6);                        // ray.py:555
-            memcpy(pn + 2 * rowb + 3, hold ? kLut6[hold] : kWhite6, 6);   // ray.py:556-557
+            store6(pn + rowb + 3, kWhite);                        // ray.py:555
+            store6(pn + 2 * rowb + 3, hold ? hold : kWhite);      // ray.py:556-557
         }
     };
     const auto t_begin = std::chrono::steady_clock::now();
@@ -419,10 +528,61 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
         e->tr_total += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
         e->tr_steps++;
     }
-    if (rc) return rc;
+    if (rc) { e->mirror_obs = nullptr; return rc; }
     if (failed.load()) {
+        e->mirror_obs = nullptr;
         cudaError_t ce = cudaStreamSynchronize(s);
         return (int)(ce != cudaSuccess ? ce : cudaErrorUnknown);
+    }
+    return 0;
+}
+
+// device-consumer transport, K >= 1 consecutive steps: K chained launches of the fused kernel (the frame buffers rotate), each
+// storing one status byte per world into mapped host memory the moment that world has stepped.  The host zeroes the bytes,
+// enqueues the launches and unpacks reward / done row by row as the bytes arrive; it returns after the LAST step's bytes --
+// the frames keep draining on the stream (cw_host_sync, or stream order for a device consumer).
+static int host_steps_device(CwHostEnv* e, const uint8_t* act_host, bool act_mapped, int32_t* reward_host, uint8_t* done_host, int K) {
+    cudaStream_t s = e->streams[0];
+    const int64_t n = e->st.n;
+    const size_t stride = ((size_t)n + 63) & ~(size_t)63;
+    int rc = ensure_pinned(&e->h_status, &e->h_status_bytes, (size_t)K * stride + (act_mapped ? 0 : (size_t)K * n));
+    if (rc) return rc;
+    memset(e->h_status, 0, (size_t)K * stride);
+    const uint8_t* act_dev = act_host;                            // (UVA: a page-locked host address is valid on the device)
+    if (!act_mapped) { uint8_t* a = e->h_status + (size_t)K * stride; memcpy(a, act_host, (size_t)K * n); act_dev = a; }
+    const auto t_begin = std::chrono::steady_clock::now();
+    static const bool nostatus = getenv("CW_HOST_NOSTATUS") && *getenv("CW_HOST_NOSTATUS") == '1';   // (experiment: cost of the status bytes)
+    if (nostatus) {
+        for (int k = 0; k < K; k++) {
+            e->cur = (e->cur + 1) % e->nring;
+            rc = cw::step_render_chained_notify(&e->cfg, &e->st, act_dev + (size_t)k * n, e->d_reward, e->d_done, e->d_obs[e->cur], e->d_goal_obs,
+                                                nullptr, e->d_stats, e->flags & CW_F_AUTO_RESET, e->d_chain, e->chain_pos, e->nring, nullptr, s);
+            if (rc) return rc;
+            e->chain_pos = (e->chain_pos + 1) % CW_CHAIN_MAX_POS;
+        }
+        CK(cudaStreamSynchronize(s));
+        return 0;
+    }
+    for (int k = 0; k < K; k++) {
+        e->cur = (e->cur + 1) % e->nring;
+        rc = cw::step_render_chained_notify(&e->cfg, &e->st, act_dev + (size_t)k * n, nullptr, nullptr, e->d_obs[e->cur], e->d_goal_obs,
+                                            nullptr, e->d_stats, e->flags & CW_F_AUTO_RESET, e->d_chain, e->chain_pos, e->nring,
+                                            e->h_status + (size_t)k * stride, s);
+        if (rc) { e->chain_pos = 0; return rc; }
+        e->chain_pos = (e->chain_pos + 1) % CW_CHAIN_MAX_POS;
+    }
+    const auto t_launched = std::chrono::steady_clock::now();
+    for (int k = 0; k < K; k++) {
+        rc = collect_status(e->h_status + (size_t)k * stride, n, e->cfg.max_steps, reward_host + (size_t)k * n, done_host + (size_t)k * n, s,
+                            (e->trace && K == 1) ? &e->tr_first_byte : nullptr);
+        if (rc) { e->chain_pos = 0; return rc; }
+    }
+    if (e->trace && K == 1) {
+        const auto t_end = std::chrono::steady_clock::now();
+        e->tr_launch += std::chrono::duration<double, std::micro>(t_launched - t_begin).count();
+        e->tr_first += std::chrono::duration<double, std::micro>(t_end - t_launched).count();
+        e->tr_total += std::chrono::duration<double, std::micro>(t_end - t_begin).count();
+        e->tr_steps++;
     }
     return 0;
 }
@@ -432,47 +592,63 @@ int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host
     if (!actions_host || !reward_host || !done_host) return CW_E_NULLPTR;
     CK(cudaSetDevice(e->device));
     const int64_t n = e->st.n;
-    const uint8_t* act_src = actions_host;
-    if (actions_host != e->pinned_actions) {                     // the attribute query costs ~1 us: remember a pinned buffer
-        if (is_pinned(actions_host)) e->pinned_actions = actions_host;
-        else { memcpy(e->h_actions, actions_host, n); act_src = e->h_actions; }
+    // An action array declared with cw_host_bind_actions and found page-locked is read in place (zero-copy); anything else goes
+    // through the handle's own pinned staging -- no pointer is ever assumed to be pinned because it once was.
+    const bool act_direct = actions_host == e->b_actions.host && e->b_actions.dev;
+    const uint8_t* act_src = actions_host;                        // readable by the host AND (mapped) by the device
+    if (!act_direct) { memcpy(e->h_actions, actions_host, n); act_src = e->h_actions; }
+    if (e->flags & CW_F_DELTA_TRANSPORT) {
+        // a delta handle keeps the caller's frame AND goal mirrors current by records alone (no device frames exist that could
+        // refresh the goal mirror), so every step of it must be a delta step
+        if (!obs_host) return CW_E_BADCONFIG;
+        return host_step_delta(e, act_src, reward_host, done_host, obs_host);
     }
-    if (obs_host && (e->flags & CW_F_DELTA_TRANSPORT)) return host_step_delta(e, act_src, reward_host, done_host, obs_host);
-    const bool direct = obs_host && is_pinned(obs_host);
+    if (!obs_host) return host_steps_device(e, act_src, true, reward_host, done_host, 1);
+    // frames transport: every frame crosses PCIe; slices alternate between two streams so copies overlap kernels
     uint8_t* frames_dst = obs_host;
-    if (obs_host && !direct) { int rc = ensure_frame_staging(e); if (rc) return rc; frames_dst = e->h_frames; }
-    if (!obs_host) {
-        // Frames stay in HBM for a device-side consumer.  Zero-copy: the kernel reads the actions from, and writes
-        // reward/done to, mapped pinned host memory (UVA), so a step is ONE launch + ONE stream sync -- no memcpy
-        // launches on the critical path.
-        cudaStream_t s = e->streams[0];
-        int rc = cw_step_render(&e->cfg, &e->st, act_src /* pinned: the caller's own buffer or our staging copy */, e->h_reward, e->h_done, e->d_obs, e->d_goal_obs, nullptr,
+    const bool direct = device_alias(obs_host) != nullptr;
+    if (!direct) { int rc = ensure_frame_staging(e); if (rc) return rc; frames_dst = e->h_frames; }
+    e->chain_pos = 0; e->cur = 0;
+    int k = 0;
+    for (int64_t off = 0; off < n; off += e->slice, k ^= 1) {
+        const int64_t cnt = (n - off) < e->slice ? (n - off) : e->slice;
+        cudaStream_t s = e->streams[k];
+        CK(cudaMemcpyAsync(e->d_actions + off, act_src + off, cnt, cudaMemcpyHostToDevice, s));
+        CwState sl = slice_state(e, off, cnt);
+        int rc = cw_step_render(&e->cfg, &sl, e->d_actions + off, e->d_reward + off, e->d_done + off,
+                                e->d_obs[0] + (size_t)off * e->frame_bytes, e->d_goal_obs + (size_t)off * e->frame_bytes, nullptr,
                                 e->d_stats, e->flags & CW_F_AUTO_RESET, s);
         if (rc) return rc;
-        CK(cudaStreamSynchronize(s));
-    } else {
-        int k = 0;
-        for (int64_t off = 0; off < n; off += e->slice, k ^= 1) {
-            const int64_t cnt = (n - off) < e->slice ? (n - off) : e->slice;
-            cudaStream_t s = e->streams[k];
-            CK(cudaMemcpyAsync(e->d_actions + off, act_src + off, cnt, cudaMemcpyHostToDevice, s));
-            CwState sl = slice_state(e, off, cnt);
-            int rc = cw_step_render(&e->cfg, &sl, e->d_actions + off, e->d_reward + off, e->d_done + off,
-                                    e->d_obs + (size_t)off * e->frame_bytes, e->d_goal_obs + (size_t)off * e->frame_bytes, nullptr,
-                                    e->d_stats, e->flags & CW_F_AUTO_RESET, s);
-            if (rc) return rc;
-            CK(cudaMemcpyAsync(e->h_reward + off, e->d_reward + off, cnt * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(e->h_done + off, e->d_done + off, cnt, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(frames_dst + (size_t)off * e->frame_bytes, e->d_obs + (size_t)off * e->frame_bytes,
-                               (size_t)cnt * e->frame_bytes, cudaMemcpyDeviceToHost, s));
-        }
-        CK(cudaStreamSynchronize(e->streams[0]));
-        CK(cudaStreamSynchronize(e->streams[1]));
+        CK(cudaMemcpyAsync(e->h_reward + off, e->d_reward + off, cnt * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(e->h_done + off, e->d_done + off, cnt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(frames_dst + (size_t)off * e->frame_bytes, e->d_obs[0] + (size_t)off * e->frame_bytes,
+                           (size_t)cnt * e->frame_bytes, cudaMemcpyDeviceToHost, s));
     }
+    CK(cudaStreamSynchronize(e->streams[0]));
+    CK(cudaStreamSynchronize(e->streams[1]));
     memcpy(reward_host, e->h_reward, n * 4);
     memcpy(done_host, e->h_done, n);
-    if (obs_host && !direct) memcpy(obs_host, e->h_frames, (size_t)n * e->frame_bytes);
+    if (!direct) memcpy(obs_host, e->h_frames, (size_t)n * e->frame_bytes);
     return 0;
+}
+
+int cw_host_step_many(CwHostEnv* e, const uint8_t* actions_host, int K, int32_t* reward_host, uint8_t* done_host, uint8_t* obs_host) {
+    if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
+    if (K < 0) return CW_E_BADCONFIG;
+    if (K == 0) return 0;
+    if (!actions_host || !reward_host || !done_host) return CW_E_NULLPTR;
+    const int64_t n = e->st.n;
+    if (obs_host) {                                               // host frames: K single steps (the frames after the last one remain)
+        for (int k = 0; k < K; k++) {
+            int rc = cw_host_step(e, actions_host + (size_t)k * n, reward_host + (size_t)k * n, done_host + (size_t)k * n, obs_host);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    if (e->flags & CW_F_DELTA_TRANSPORT) return CW_E_BADCONFIG;   // (see cw_host_step)
+    CK(cudaSetDevice(e->device));
+    // open-loop run for a device consumer: K chained launches enqueued back to back, reward / done rows unpacked as they land
+    return host_steps_device(e, actions_host, device_alias(actions_host) != nullptr, reward_host, done_host, K);
 }
 
 int cw_host_stats(CwHostEnv* e, int64_t* stats_host) {
@@ -492,7 +668,25 @@ int cw_host_stats(CwHostEnv* e, int64_t* stats_host) {
 int cw_host_device_state(CwHostEnv* e, CwState* out_state, uint8_t** out_obs) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     if (out_state) *out_state = e->st;
-    if (out_obs) *out_obs = e->d_obs;
+    if (out_obs) *out_obs = e->d_obs[e->cur];
+    return 0;
+}
+
+int cw_host_fetch_frames(CwHostEnv* e, uint8_t* obs_host, uint8_t* goal_obs_host) {
+    if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
+    if (e->flags & CW_F_DELTA_TRANSPORT) return CW_E_BADCONFIG;   // a delta handle has no current device frames
+    CK(cudaSetDevice(e->device));
+    const size_t total = (size_t)e->st.n * e->frame_bytes;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, e->d_obs[e->cur], total, cudaMemcpyDeviceToHost, e->streams[0]));
+    if (goal_obs_host) CK(cudaMemcpyAsync(goal_obs_host, e->d_goal_obs, total, cudaMemcpyDeviceToHost, e->streams[0]));
+    CK(cudaStreamSynchronize(e->streams[0]));
+    return 0;
+}
+
+int cw_host_stream(CwHostEnv* e, void** out_stream) {
+    if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
+    if (!out_stream) return CW_E_NULLPTR;
+    *out_stream = (void*)e->streams[0];
     return 0;
 }
 
@@ -500,18 +694,18 @@ int cw_host_destroy(CwHostEnv* e) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     cudaSetDevice(e->device);
     if (e->trace && e->tr_steps)
-        fprintf(stderr, "cw_host trace: %llu delta steps; launch call %.2f us, launch -> first record %.2f us, whole call %.2f us\n",
-                (unsigned long long)e->tr_steps, e->tr_launch / e->tr_steps, e->tr_first / e->tr_steps, e->tr_total / e->tr_steps);
-    if (e->streams[0]) cudaStreamSynchronize(e->streams[0]);     // the delta path returns without a stream sync
+        fprintf(stderr, "cw_host trace: %llu calls; launch call(s) %.2f us, launch -> first record / all status bytes %.2f us (first byte %.2f us), whole call %.2f us\n",
+                (unsigned long long)e->tr_steps, e->tr_launch / e->tr_steps, e->tr_first / e->tr_steps, e->tr_first_byte / e->tr_steps, e->tr_total / e->tr_steps);
+    if (e->streams[0]) cudaStreamSynchronize(e->streams[0]);     // neither fast path ends with a stream sync
     if (e->streams[1]) cudaStreamSynchronize(e->streams[1]);
     cudaFree(e->st.grid); cudaFree(e->st.init_grid); cudaFree(e->st.agent); cudaFree(e->st.goal); cudaFree(e->st.t);
-    cudaFree(e->st.episode); cudaFree(e->d_actions); cudaFree(e->d_reward); cudaFree(e->d_obs);
-    cudaFree(e->d_goal_obs); cudaFree(e->d_stats);
+    cudaFree(e->st.episode); cudaFree(e->d_actions); cudaFree(e->d_reward); for (int i = 0; i < 4; i++) cudaFree(e->d_obs[i]);
+    cudaFree(e->d_goal_obs); cudaFree(e->d_stats); cudaFree(e->d_chain);
     cudaFreeHost(e->h_actions); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_stats);
+    if (e->h_status) cudaFreeHost(e->h_status);
     if (e->h_frames) cudaFreeHost(e->h_frames);
     if (e->h_delta) cudaFreeHost(e->h_delta);
     if (e->h_fresh) cudaFreeHost(e->h_fresh);
-    free(e->m_grid); free(e->m_agent);
     delete e->pool;
     if (e->streams[0]) cudaStreamDestroy(e->streams[0]);
     if (e->streams[1]) cudaStreamDestroy(e->streams[1]);

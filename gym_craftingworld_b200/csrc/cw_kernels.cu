@@ -22,6 +22,7 @@
 
 #include "cw_b200.h"
 #include "cw_device.cuh"
+#include "cw_internal.h"
 
 namespace cw {
 
@@ -38,10 +39,12 @@ struct EnvArgs {
     uint8_t* goal_obs;
     uint8_t* init_obs;       // INIT_OBS copy of the first frame of a new episode (ray.py:193), nullable
     unsigned long long* stats;
-    uint4* delta;            // delta transport: per-world record {agent, goal, wcell | wval<<16 | flags<<24, reward} (nullable)
-    uint32_t* fresh;         // delta transport: [N][CW_FRESH_WORDS] sparse record of a re-seeded world + its imagined goal
     uint32_t* list;          // work-list launch (cw_step_render_edit): [0] count, [1] exit ticket, [2..] world ids to re-seed
-    uint32_t delta_seq;      // delta transport: 6-bit sequence tag stored in bits 2..7 of the record's flag byte
+    // host-buffer API (chained launches): one self-validating status byte per world, 0x80 | success << 1 | done, stored into
+    // mapped pinned host memory the moment the world has stepped -- long before its frame is composed.  The host zeroes the
+    // bytes before the launch and polls them: no fence, no counter, no stream synchronisation (a system-scope fence issued
+    // while the SM streams frames out was measured to return only when the launch was all but over).
+    uint8_t* status;
     const uint8_t* rgrid;    // render-only entry: grid / agent given directly (state may be partial)
     const uint32_t* ragent;
     int mode;
@@ -70,14 +73,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// spin until *p >= want.  A chain that was set up wrongly must not hang the GPU: after 2 s the kernel traps.
+// spin until *p >= want.  A chain that was set up wrongly must not hang the GPU for ever: after g_chain_timeout_ns (10 s unless
+// CW_CHAIN_TIMEOUT_MS says otherwise; a legitimately slow predecessor under a debugger / sanitizer / time-slicing needs far
+// less, and CW_NO_CHAIN=1 turns chained launches into ordinary ones for such sessions) the kernel traps -- loudly, instead of
+// returning frames that were never produced.
+__device__ unsigned long long g_chain_timeout_ns = 10000000000ull;
 __device__ __forceinline__ void chain_wait_ge(const uint32_t* p, uint32_t want) {
     if (ld_acquire_gpu(p) >= want) return;
     const unsigned long long t0 = global_timer_ns();
     for (;;) {
         __nanosleep(64);
         if (ld_acquire_gpu(p) >= want) return;
-        if (global_timer_ns() - t0 > 2000000000ull) __trap();
+        if (global_timer_ns() - t0 > g_chain_timeout_ns) __trap();
     }
 }
 
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     constexpr bool kChained = kVariant == V_CHAINED, kList = kVariant == V_LIST;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_lut[9];
-    __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32], s_ep[32], s_rew[32];
+    __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32], s_ep[32];
     __shared__ uint32_t s_flag[32];
     __shared__ uint32_t s_obj[8];
     __shared__ uint32_t s_anypend;
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
             const int lane = tid;
             const int64_t e = e0 + lane;
             const bool valid = lane < G && e < st.n;
-            uint32_t agent = c_agent, goal = c_goal, flag = 0, rew_stash = 0;
+            uint32_t agent = c_agent, goal = c_goal, flag = 0;
             if (valid) {
                 const bool skip = (mode & M_FORCE_RESET) && !c_forced;   // masked reset: untouched worlds are skipped
                 if (!skip && (mode & M_RENDER)) flag |= FL_RENDER;
@@ -280,19 +287,18 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     if (wcell >= 0) st.grid[e * cs + wcell] = (uint8_t)wval;
                     if (args.reward) args.reward[e] = rew;
                     if (args.done) args.done[e] = dn ? 1 : 0;
+                    if constexpr (!kList) {
+                        if (args.status) args.status[e] = (uint8_t)(0x80u | (rew == cfg.max_steps ? 2u : 0u) | (dn ? 1u : 0u));
+                    }
                     if (dn && (mode & M_AUTO_RESET)) {
                         flag |= FL_PENDING;
                         if (args.stats) stats_add(cfg, args.stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
                     } else {
                         st.agent[e] = agent; st.goal[e] = goal; st.t[e] = t;
-                        if (args.delta)                           // one 16-byte store (possibly into mapped host memory)
-                            args.delta[e] = make_uint4(agent, goal, (uint32_t)(wcell & 0xFFFF) | ((uint32_t)wval << 16) |
-                                                       (((dn ? 1u : 0u) | (args.delta_seq << 2)) << 24), (uint32_t)rew);
                     }
-                    rew_stash = (uint32_t)rew;
                 }
             }
-            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; s_ep[lane] = c_ep; s_rew[lane] = rew_stash; }
+            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; s_ep[lane] = c_ep; }
             const uint32_t pend = __ballot_sync(0xffffffffu, (flag & FL_PENDING) != 0);
             if (lane == 0) s_anypend = pend;
         }
@@ -318,30 +324,9 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     if (lane == 0) { st.agent[er] = ag; st.goal[er] = gl; st.t[er] = 0; s_agent[i] = ag; }
                     flag |= FL_FRESH;
                     if (lane == 0 && st.init_agent) st.init_agent[er] = ag;
-                    if (args.delta) {                             // delta transport: the new world as a sparse list
-                        uint32_t* fr = args.fresh + (size_t)er * CW_FRESH_WORDS;
-                        uint32_t word = 0;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) word = lane == k ? (objs.cell[k] | (objs.code[k] << 16)) : word;
-                        if (lane < 8) fr[lane] = word;
-                    }
-                    if (args.goal_obs || st.goal_grid || args.delta) {   // desired_goal = imagine_obs(): ray.py:191, 220-299
+                    if (args.goal_obs || st.goal_grid) {          // desired_goal = imagine_obs(): ray.py:191, 220-299
                         uint32_t gag = ag;
                         imagine_fresh(cfg, objs, gag, gl >> 16, rng);      // closed form on the 8-object list
-                        if (args.delta) {
-                            uint32_t* fr = args.fresh + (size_t)er * CW_FRESH_WORDS;
-                            uint32_t word = 0;
-#pragma unroll
-                            for (int k = 0; k < 8; k++) word = lane == k ? (objs.cell[k] | (objs.code[k] << 16)) : word;
-                            if (lane < 8) fr[8 + lane] = word;
-                            if (lane == 8) fr[16] = gag;
-                            // the 16-byte record goes LAST: a consumer polling its sequence tag (possibly the host, through
-                            // mapped memory) must find the sparse record complete
-                            __threadfence_system();
-                            __syncwarp();
-                            if (lane == 0)
-                                args.delta[er] = make_uint4(ag, gl, 0xFFFFu | ((3u /* done | fresh */ | (args.delta_seq << 2)) << 24), s_rew[i]);
-                        }
                         tile_from_objects(objs, nchunk16, simag + i * cs);
                         if (st.goal_grid) {                       // compact goal state (one-hot observation family)
                             for (int ch = lane; ch < nchunk16; ch += 32)
@@ -410,13 +395,19 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     cp_async_wait<0>();
     if (tid == 0) {
         bulk_wait_all();
-        if (chained) { __threadfence(); atomicAdd(c_fin + cpos, 1u); }   // this CTA's frames of chain position cpos are complete
+        if (chained) {                                            // this CTA's frames of chain position cpos are complete
+            __threadfence();
+            const uint32_t before = atomicAdd(c_fin + cpos, 1u);
+            // The grid must not COMPLETE before its predecessor grid has (whatever follows the chain in the stream sees all of
+            // it).  ONE resident thread is enough for that -- the last CTA out; if every CTA waited here, each would hold its
+            // SM slot and shared memory until the predecessor's completion flush, delaying the launch after this one.
+            if (chain_follow && before == gridDim.x - 1) pdl_wait();
+        }
         if (kList) {                                              // the last CTA out (all have read the count) empties the list
             __threadfence();
             if (atomicAdd(args.list + 1, 1u) == gridDim.x - 1) { args.list[0] = 0; args.list[1] = 0; }
         }
     }
-    if (chain_follow) pdl_wait();                                 // do not COMPLETE before the predecessor grid has
     CW_STAMP(7);
 }
 
@@ -550,14 +541,17 @@ __global__ void __launch_bounds__(128) cw_delta_kernel(const CwConfig cfg, const
         const int a = kInParams ? pa.a[n] : actions[n];           // (host-mapped memory: the longest latency, issued first)
         agent = __ldcg(st.agent + n); goal = __ldcg(st.goal + n); t = __ldcg(st.t + n);
         ep = (flags & CW_F_AUTO_RESET) ? __ldcg(st.episode + n) : 0u;
-        int wcell, wval;
-        const int rew = step_core<true>(cfg, g, st.init_grid + nn * cfg.cell_stride, agent, goal, t, a, dn, wcell, wval);
+        int wcell, wval, ocode, ncode;
+        const uint32_t opos = (agent & 0x3Fu) | (((agent >> 8) & 0x3Fu) << 6);   // where the agent stood (row | col << 6)
+        const int rew = step_core_ex<true>(cfg, g, st.init_grid + nn * cfg.cell_stride, agent, goal, t, a, dn, wcell, wval, ocode, ncode);
         rew_u = (uint32_t)rew;
         if (dn && (flags & CW_F_AUTO_RESET)) {
             if (stats) stats_add(cfg, stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
         } else {
             st.agent[n] = agent; st.goal[n] = goal; st.t[n] = t;
-            delta[n] = make_uint4(agent, goal, (uint32_t)(wcell & 0xFFFF) | ((uint32_t)wval << 16) | (((dn ? 1u : 0u) | (seq << 2)) << 24), rew_u);
+            // the record is pre-digested: the consumer repaints from it alone (no copy of the grid on its side)
+            delta[n] = make_uint4(agent, goal, opos | ((uint32_t)ocode << 12) | ((uint32_t)ncode << 16) | (wcell >= 0 ? 1u << 20 : 0u) |
+                                  (((dn ? 1u : 0u) | (seq << 2)) << 24), rew_u);
         }
     }
     if (!(flags & CW_F_AUTO_RESET)) return;
@@ -587,7 +581,7 @@ __global__ void __launch_bounds__(128) cw_delta_kernel(const CwConfig cfg, const
         if (lane == 8) fr[16] = gag;
         __threadfence_system();                                   // the 16-byte record goes last (see cw_env_kernel)
         __syncwarp();
-        if (lane == 0) delta[env] = make_uint4(ag, gl, 0xFFFFu | ((3u /* done | fresh */ | (seq << 2)) << 24), env_rew);
+        if (lane == 0) delta[env] = make_uint4(ag, gl, (3u /* done | fresh */ | (seq << 2)) << 24, env_rew);
     }
 }
 
@@ -878,7 +872,8 @@ struct Tunables {
     int bands_per_chunk = env_int("CW_BANDS_PER_CHUNK", 0), chunk_bytes = env_int("CW_CHUNK_BYTES", 25 * 1024);
     int frame_buffers = env_int("CW_FRAME_BUFFERS", 0), first_split = env_int("CW_FIRST_SPLIT", 4);
     int ctas_per_sm = env_int("CW_CTAS_PER_SM", 0), group = env_int("CW_GROUP", 0);
-    int delta_env_kernel = env_int("CW_DELTA_ENV_KERNEL", 0);   // 1: cw_step_delta through the fused kernel (the older path)
+    int no_chain = env_int("CW_NO_CHAIN", 0);                   // 1: cw_step_render_chained degrades to ordinary launches
+    int chain_timeout_ms = env_int("CW_CHAIN_TIMEOUT_MS", 0);   // > 0: spin limit of the chain waits
 };
 static const Tunables& tunables() {
     static const Tunables t;
@@ -967,12 +962,50 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     int64_t blocks = (int64_t)dev->sms * best_per_sm;
     const int64_t groups = (st->n + bestG - 1) / bestG;
     if (blocks > groups) blocks = groups;                         // (work-list launch: the count lives on the device; groups == n)
+    if (args.chain && tunables().chain_timeout_ms > 0) {          // once: the spin limit of the chain waits
+        static std::once_flag once;
+        std::call_once(once, [] {
+            const unsigned long long ns = (unsigned long long)tunables().chain_timeout_ms * 1000000ull;
+            cudaMemcpyToSymbol(g_chain_timeout_ns, &ns, sizeof(ns));
+        });
+    }
     if (args.chain && args.chain_pos == 0) {                      // a chain opens: clear its counters and epoch words
         cudaError_t me = cudaMemsetAsync(args.chain, 0, sizeof(uint32_t) * (size_t)(CW_CHAIN_MAX_POS + st->n), stream);
         if (me != cudaSuccess) return (int)me;
     }
     cudaError_t le = launch_pdl(kern, dim3((unsigned)blocks), dim3(kEnvThreads), smem, stream, *cfg, *st, args);
     return (int)(le != cudaSuccess ? le : cudaGetLastError());
+}
+
+
+static int check_state(const CwState* st) {
+    if (!st) return CW_E_NULLPTR;
+    if (st->n < 0) return CW_E_BADCONFIG;
+    if (st->n > 0 && (!st->grid || !st->init_grid || !st->agent || !st->goal || !st->t || !st->episode)) return CW_E_NULLPTR;
+    if (st->n_fixed < 0 || (st->n_fixed > 0 && (!st->fixed_grid || !st->fixed_agent))) return CW_E_NULLPTR;
+    if (st->goal_grid && !st->goal_agent) return CW_E_NULLPTR;
+    return 0;
+}
+
+int step_render_chained_notify(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
+                               uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, uint32_t* chain,
+                               int chain_pos, int obs_ring, uint8_t* status, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    rc = check_state(st); if (rc) return rc;
+    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
+    if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
+    if (chain_pos < 0 || chain_pos >= CW_CHAIN_MAX_POS || obs_ring < 1) return CW_E_BADCONFIG;
+    if (st->n == 0) return 0;
+    if (!actions || !obs || !chain) return CW_E_NULLPTR;
+    if (!status && (!reward || !done)) return CW_E_NULLPTR;
+    EnvArgs a = {};
+    a.actions = actions; a.reward = reward; a.done = done; a.obs = obs; a.goal_obs = goal_obs; a.init_obs = init_obs;
+    a.stats = (unsigned long long*)stats;
+    a.mode = M_STEP | M_RENDER | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
+    a.status = status;
+    if (tunables().no_chain) return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);   // (debugger / sanitizer sessions, experiments)
+    a.chain = chain; a.chain_pos = chain_pos; a.chain_ring = obs_ring;
+    return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
 }
 
 }  // namespace cw
@@ -998,14 +1031,6 @@ const char* cw_error_string(int code) {
     }
 }
 
-static int check_state(const CwState* st) {
-    if (!st) return CW_E_NULLPTR;
-    if (st->n < 0) return CW_E_BADCONFIG;
-    if (st->n > 0 && (!st->grid || !st->init_grid || !st->agent || !st->goal || !st->t || !st->episode)) return CW_E_NULLPTR;
-    if (st->n_fixed < 0 || (st->n_fixed > 0 && (!st->fixed_grid || !st->fixed_agent))) return CW_E_NULLPTR;
-    if (st->goal_grid && !st->goal_agent) return CW_E_NULLPTR;
-    return 0;
-}
 
 int cw_reset(const CwConfig* cfg, const CwState* st, const uint8_t* mask, uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs,
              void* stream) {
@@ -1093,19 +1118,8 @@ int cw_step_render(const CwConfig* cfg, const CwState* st, const uint8_t* action
 int cw_step_render_chained(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
                            uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, uint32_t* chain,
                            int chain_pos, int obs_ring, void* stream) {
-    int rc = check_config(cfg); if (rc) return rc;
-    rc = check_state(st); if (rc) return rc;
-    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
-    if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
-    if (chain_pos < 0 || chain_pos >= CW_CHAIN_MAX_POS || obs_ring < 1) return CW_E_BADCONFIG;
-    if (st->n == 0) return 0;
-    if (!actions || !reward || !done || !obs || !chain) return CW_E_NULLPTR;
-    EnvArgs a = {};
-    a.actions = actions; a.reward = reward; a.done = done; a.obs = obs; a.goal_obs = goal_obs; a.init_obs = init_obs;
-    a.stats = (unsigned long long*)stats;
-    a.mode = M_STEP | M_RENDER | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
-    a.chain = chain; a.chain_pos = chain_pos; a.chain_ring = obs_ring;
-    return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
+    return cw::step_render_chained_notify(cfg, st, actions, reward, done, obs, goal_obs, init_obs, stats, flags, chain, chain_pos,
+                                          obs_ring, nullptr, stream);
 }
 
 int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions, void* delta, uint32_t* fresh, int64_t* stats,
@@ -1117,28 +1131,21 @@ int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions
     if (st->n == 0) return 0;
     if (!actions || !delta || !fresh) return CW_E_NULLPTR;
     if (seq < 0 || seq > 63) return CW_E_BADCONFIG;
-    if (!st->goal_grid && tunables().delta_env_kernel == 0) {     // the latency path (the fused kernel remains for goal_grid users / A-B)
-        const int64_t blocks = (st->n + 127) / 128;
-        const int kflags = flags & CW_F_AUTO_RESET;
-        cudaError_t le;
-        if ((flags & CW_F_HOST_ACTIONS) && st->n <= kParamActions) {   // small batch, actions readable here: ship them in the launch
-            static thread_local ActionBlock blk;
-            memcpy(blk.a, actions, (size_t)st->n);
-            le = launch_pdl(cw_delta_kernel<true>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions, blk,
-                            (uint4*)delta, fresh, (unsigned long long*)stats, (uint32_t)seq, kflags);
-        } else {
-            static const ActionBlock none = {};
-            le = launch_pdl(cw_delta_kernel<false>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions, none,
-                            (uint4*)delta, fresh, (unsigned long long*)stats, (uint32_t)seq, kflags);
-        }
-        return (int)(le != cudaSuccess ? le : cudaGetLastError());
+    if (st->goal_grid) return CW_E_BADCONFIG;                     // the compact goal state is maintained by cw_reset / cw_step_render only
+    const int64_t blocks = (st->n + 127) / 128;
+    const int kflags = flags & CW_F_AUTO_RESET;
+    cudaError_t le;
+    if ((flags & CW_F_HOST_ACTIONS) && st->n <= kParamActions) {   // small batch, actions readable here: ship them in the launch
+        static thread_local ActionBlock blk;
+        memcpy(blk.a, actions, (size_t)st->n);
+        le = launch_pdl(cw_delta_kernel<true>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions, blk,
+                        (uint4*)delta, fresh, (unsigned long long*)stats, (uint32_t)seq, kflags);
+    } else {
+        static const ActionBlock none = {};
+        le = launch_pdl(cw_delta_kernel<false>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions, none,
+                        (uint4*)delta, fresh, (unsigned long long*)stats, (uint32_t)seq, kflags);
     }
-    EnvArgs a = {};
-    a.delta_seq = (uint32_t)seq;
-    a.actions = actions; a.delta = (uint4*)delta; a.fresh = fresh; a.stats = (unsigned long long*)stats;
-    a.reward = nullptr; a.done = nullptr;
-    a.mode = M_STEP | ((flags & CW_F_AUTO_RESET) ? M_AUTO_RESET : 0);
-    return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
+    return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 int cw_imagine(const CwConfig* cfg, const CwState* st, uint8_t* goal_obs, void* stream) {

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define CW_ABI_VERSION 2
+#define CW_ABI_VERSION 3
 #define CW_STATS_LEN 24
 #define CW_STATS_REPLICAS 16 /* the stats buffer is int64[CW_STATS_REPLICAS][CW_STATS_LEN]: finished episodes are added to
                                 replica (block index % 16) so same-address atomics do not serialise; consumers sum the replicas */
@@ -160,15 +160,19 @@ int cw_step_render_chained(const CwConfig* cfg, const CwState* st, const uint8_t
                            int chain_pos, int obs_ring, void* stream);
 
 /* step + auto-reset WITHOUT device frames, for a host-side frame mirror ("delta transport"): instead of 48*H*W bytes of
- * pixels per world, each world gets one 16-byte record, written with ONE 16-byte store
- *     delta[n] = { agent, goal, wcell | wval<<16 | flags<<24, reward }      flags: 1 done, 2 fresh (re-seeded),
- *                                                                            bits 2..7 = `seq` (0..63), the caller's tag
- * (wcell = 0xFFFF: no grid cell written this step), and a world re-seeded in this call additionally gets (written and
- * fenced system-wide BEFORE its delta record, so a consumer that polls the tag finds them complete)
+ * pixels per world, each world gets one PRE-DIGESTED 16-byte record, written with ONE 16-byte store
+ *     delta[n] = { agent, goal, digest, reward }
+ *     digest   = orow | ocol<<6 | ocode<<12 | ncode<<16 | objchg<<20 | flags<<24
+ *                (orow, ocol) where the agent stood before the step; ocode / ncode the object codes -- after the step -- of that
+ *                cell and of the cell it stands on now (`agent`); objchg: the object under the agent changed (pickup, drop, a
+ *                transforming move); flags: 1 done, 2 fresh (re-seeded), bits 2..7 = `seq` (0..63), the caller's tag.
+ * Everything render_edit (ray.py:522-557) needs is in the record, so the consumer keeps no copy of the grid.  A world
+ * re-seeded in this call additionally gets (written and fenced system-wide BEFORE its delta record, so a consumer that polls
+ * the tag finds them complete)
  *     fresh[n][0..7]  = cell | code<<16 of its 8 objects        fresh[n][8..15] = same for the imagined goal state
  *     fresh[n][16]    = agent word of the imagined goal state
- * `delta` / `fresh` may point into mapped pinned HOST memory (zero-copy): the consumer patches the <= 3 cells that changed
- * in its own copy of the frame (what the reference's render_edit does, ray.py:522-557). */
+ * `delta` / `fresh` may point into mapped pinned HOST memory (zero-copy).  st->goal_grid must be NULL (the compact goal state
+ * is maintained by cw_reset / cw_step_render only). */
 int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions, void* delta /* uint4[N] */,
                   uint32_t* fresh /* [N][CW_FRESH_WORDS] */, int64_t* stats, int flags, int seq, void* stream);
 
@@ -193,22 +197,54 @@ int cw_render_alt(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agen
                   void* stream);
 
 /* ---- host-buffer API: the env behind an opaque handle, all arguments HOST pointers ----------------------
- * The drop-in for a host-language caller without device memory of its own: the library owns the device state,
- * pinned staging buffers and streams; each call copies actions host->device, runs the fused launch(es) in
- * slices, and copies reward/done (and obs if non-NULL) device->host, overlapping copies with compute.
- * Calls on one handle are not re-entrant (like the reference env object). */
+ * The drop-in for a host-language caller without device memory of its own: the library owns the device state, pinned
+ * staging buffers and streams.  One cw_host_step = one reference-style `obs, reward, done, info = env.step(action)`
+ * (ray.py:301-378) for N worlds.  Calls on one handle are not re-entrant (like the reference env object).
+ *
+ * Where the frames go is chosen per handle / per call:
+ *   obs_host == NULL            DEVICE CONSUMER: the fused step + auto-reset + render kernel leaves the frames in HBM (two
+ *                               alternating buffers, cw_host_device_state); only actions (in) and reward / done (out) cross
+ *                               PCIe, through mapped pinned memory (one status byte per world comes back).  Launches are chained
+ *                               (cw_step_render_chained) and the call returns as soon as every world's reward / done is in host
+ *                               memory -- the frames of this step may still be draining on the handle's stream (cw_host_stream;
+ *                               cw_host_sync waits for them).
+ *   CW_F_DELTA_TRANSPORT handle HOST FRAMES by delta records: obs_host (and the goal buffer given to cw_host_reset) are
+ *                               persistent mirrors owned by the caller, pass the same pointers every call; the library patches
+ *                               them in place from 16-byte records (a different obs pointer triggers one full refresh).  After
+ *                               every call they hold exactly the frames a full device render + copy would have produced.
+ *                               Such a handle takes delta steps only (obs_host == NULL is CW_E_BADCONFIG).
+ *   otherwise                   HOST FRAMES by copy: every rendered frame crosses PCIe (sliced over two streams). */
 typedef struct CwHostEnv CwHostEnv;
 int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, uint64_t env_id_base, int flags,
                    CwHostEnv** out);
 int cw_host_reset(CwHostEnv* env, uint8_t* obs_host /*nullable*/, uint8_t* goal_obs_host /*nullable*/);
+/* Declare the caller's persistent action array (nullable to undeclare).  If it is page-locked (cudaHostAlloc, cudaHostRegister,
+ * a pinned torch tensor) the device reads it IN PLACE whenever cw_host_step is called with exactly this pointer; the caller keeps
+ * it allocated and page-locked until the next cw_host_bind_actions or cw_host_destroy.  Any other action pointer (or a pageable
+ * one) is staged through the handle's own pinned buffer on every call -- the library never assumes a buffer is page-locked
+ * because it once was.  reward / done / frame arrays may be any host memory. */
+int cw_host_bind_actions(CwHostEnv* env, const uint8_t* actions_host);
 int cw_host_step(CwHostEnv* env, const uint8_t* actions_host, int32_t* reward_host, uint8_t* done_host,
-                 uint8_t* obs_host /*nullable: pixels stay on the device*/);
-/* With CW_F_DELTA_TRANSPORT, obs_host (and the goal buffer given to cw_host_reset) are persistent mirrors owned by the
- * caller: pass the same pointers every call; the library patches them in place (a different pointer triggers one full
- * refresh).  After every call they hold exactly the frames a full device render + copy would have produced. */
+                 uint8_t* obs_host /*nullable: device consumer*/);
+/* K consecutive steps on an open-loop action tape actions_host[K][N]; reward_host / done_host are [K][N].  Device consumer
+ * (obs_host == NULL): K chained launches enqueued back to back and ONE wait -- the round trip is paid once per K steps; with
+ * obs_host the call is K cw_host_step calls (the frames after the last step remain). */
+int cw_host_step_many(CwHostEnv* env, const uint8_t* actions_host, int K, int32_t* reward_host, uint8_t* done_host,
+                      uint8_t* obs_host /*nullable*/);
+/* Inject state (each array nullable = leave as is): grid uint8[N][cell_stride] (also becomes INIT_OBS_VECTOR, ray.py:183),
+ * agent / goal words uint32[N], step counters int32[N]; obs_host (nullable) receives the frames of the new state (goal frames
+ * stay those of the last reset).  For parity tests (reference-generated states) and staggered starts. */
+int cw_host_load_state(CwHostEnv* env, const uint8_t* grid_host, const uint32_t* agent_host, const uint32_t* goal_host,
+                       const int32_t* t_host, uint8_t* obs_host /*nullable*/);
 int cw_host_stats(CwHostEnv* env, int64_t* stats_host /*[CW_STATS_LEN]*/);
-/* device pointers of the handle's state, for callers that DO have a device-side consumer (e.g. a policy) */
+/* device pointers of the handle's state and of the frame buffer holding the CURRENT observation, for callers that DO have a
+ * device-side consumer (e.g. a policy): order the consumer after the env kernels through cw_host_stream (a cudaStream_t) */
 int cw_host_device_state(CwHostEnv* env, CwState* out_state, uint8_t** out_obs);
+int cw_host_stream(CwHostEnv* env, void** out_stream);
+/* copy the CURRENT device frames (and the goal frames) to host memory, each nullable; synchronises the handle's stream.
+ * For inspection / recording by a caller whose steps leave the frames on the device (not for delta handles). */
+int cw_host_fetch_frames(CwHostEnv* env, uint8_t* obs_host, uint8_t* goal_obs_host);
+int cw_host_sync(CwHostEnv* env); /* wait for everything the handle has enqueued (frames of the last step included) */
 int cw_host_destroy(CwHostEnv* env);
 
 #ifdef __cplusplus

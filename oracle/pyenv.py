@@ -84,3 +84,31 @@ def run_worker(args):
             if done:
                 w.reset()
     return envs * steps, time.perf_counter() - t0
+
+
+def run_worker_reference(args):
+    """The same loop as :func:`run_worker` on the UNMODIFIED reference class ``CraftingWorldEnvRay``
+    (``ray.py:53-378``; ``/root/reference`` or its install under ``oracle/_ref``, see ``oracle/build_ref.py``): one
+    reference env object per world, ``env.step(a)`` then ``env.reset()`` on done (``gen_info.rst:71-80``).
+    Returns (env_steps, seconds) for the timed part."""
+    import time
+    from . import ref_shim
+    envs, steps, warmup, size, max_steps, seed = args
+    ray = ref_shim.load_reference()
+    rng = np.random.RandomState(seed)
+    worlds = []
+    for i in range(envs):
+        w = ray.CraftingWorldEnvRay(size=size, max_steps=max_steps)                  # nine-skill random tasks, stacking
+        w.seed(seed * 7919 + i)
+        w.reset()
+        worlds.append(w)
+    acts = rng.randint(0, 6, (warmup + steps, envs))
+    t0 = 0.0
+    for k in range(warmup + steps):
+        if k == warmup:
+            t0 = time.perf_counter()
+        for i, w in enumerate(worlds):
+            _, _, done, _ = w.step(int(acts[k, i]))
+            if done:
+                w.reset()
+    return envs * steps, time.perf_counter() - t0

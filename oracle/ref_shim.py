@@ -6,9 +6,10 @@ metadata only (``gym.spaces``), a base class (``gym.GoalEnv``), and the RNG fact
 (``gym.utils.seeding.np_random``; gym <= 0.21 returns a ``np.random.RandomState``).  Attribute uses:
 ``craftingworld_ray.py:1-3, 8-11, 53, 85-110, 112, 133, 146`` and ``gym_craftingworld/__init__.py:3``.
 
-The reference root is resolved from ``$CW_REFERENCE`` then ``/root/reference``.  It does not exist on the
-GPU box: callers must use :func:`reference_available` and fall back to the frozen traces in
-``tests/golden/``.
+The reference root is resolved from ``$CW_REFERENCE``, then ``/root/reference`` (the builder container), then
+``oracle/_ref`` -- the unmodified package as installed by ``oracle/build_ref.py`` (git-ignored, travels to the GPU box
+with the built ``.so`` files).  Callers must still use :func:`reference_available` and fall back to the frozen traces
+in ``tests/golden/`` when none of them exists.
 """
 from __future__ import annotations
 
@@ -18,7 +19,8 @@ import types
 
 import numpy as np
 
-_CANDIDATES = [os.environ.get("CW_REFERENCE", ""), "/root/reference"]
+_CANDIDATES = [os.environ.get("CW_REFERENCE", ""), "/root/reference",
+               os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
 
 
 def reference_root():

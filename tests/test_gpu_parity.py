@@ -558,3 +558,104 @@ def test_randomized_configurations_vs_oracle(cw):
             assert np.array_equal(env.stats.cpu().numpy(), ob.stats), where
         finally:
             native.set_fixed_pool(None)
+
+
+@pytest.mark.parametrize("size,N,max_steps", [(21, 3000, 15), (7, 130, 5), (32, 700, 20)])
+def test_host_env_device_consumer_matches_oracle(cw, size, N, max_steps):
+    """Device-consumer transport (return_frames=False): chained launches, reward / done land in mapped host memory and the
+    call returns on ONE notification word, frames stay in HBM (two alternating buffers).  reward / done after every call and
+    the device frames (fetched) every few steps must equal the oracle's."""
+    seed, K = 17, 70
+    env = cw.HostCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=seed, return_frames=False)
+    ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed)
+    env.reset()
+    o_goal = ob.reset(with_goal=True)
+    o_obs = ob.render()
+    obs, goal = env.fetch_frames()
+    assert np.array_equal(obs, o_obs) and np.array_equal(goal, o_goal)
+    rng = np.random.RandomState(3)
+    new_goal = np.zeros_like(o_goal)
+    for k in range(K):
+        a = rng.randint(0, 6, N)
+        _, reward, done, _ = env.step(a)
+        o_reward, o_done = ob.step_full(a.astype(np.uint8), auto_reset=True, obs=o_obs, goal_obs=new_goal)
+        o_goal[o_done == 1] = new_goal[o_done == 1]
+        assert np.array_equal(reward, o_reward) and np.array_equal(done, o_done.astype(bool)), k
+        if k % 7 == 6 or k == K - 1:
+            obs, goal = env.fetch_frames()
+            assert np.array_equal(obs, o_obs), f"device frames diverged at step {k}"
+            assert np.array_equal(goal, o_goal), f"device goal frames diverged at step {k}"
+    assert np.array_equal(env.stats(), ob.stats) and ob.stats[0] > 0
+    env.close()
+
+
+@pytest.mark.parametrize("frames", [False, True])
+def test_host_env_step_many_matches_oracle(cw, frames):
+    """cw_host_step_many: K steps of an open-loop tape per call (device consumer: K chained launches, one wait; more steps than
+    notification slots in one call; host frames by delta: K single steps)."""
+    N, size, max_steps, seed = 1500, 21, 12, 29
+    env = cw.HostCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=seed, return_frames=frames, transport="delta")
+    ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed)
+    env.reset(); ob.reset(with_goal=True)
+    o_obs = ob.render()
+    rng = np.random.RandomState(4)
+    for K in (1, 5, 130, 64):
+        tape = rng.randint(0, 6, (K, N)).astype(np.uint8)
+        obs, reward, done, _ = env.step_many(tape)
+        for k in range(K):
+            o_reward, o_done = ob.step_full(tape[k], auto_reset=True, obs=o_obs)
+            assert np.array_equal(reward[k], o_reward) and np.array_equal(done[k], o_done.astype(bool)), (K, k)
+        frame = obs["observation"] if frames else env.fetch_frames()[0]
+        assert np.array_equal(frame, o_obs), K
+    _, reward, done, _ = env.step(tape[0])                       # single steps and runs interleave freely
+    o_reward, o_done = ob.step_full(tape[0], auto_reset=True, obs=o_obs)
+    assert np.array_equal(reward, o_reward)
+    assert np.array_equal(env.stats(), ob.stats)
+    env.close()
+
+
+def test_host_api_unbound_pageable_buffers_and_delta_rules(cw):
+    """C ABI directly: arrays that were never declared with cw_host_bind (pageable NumPy memory, new ones every call) are staged
+    by the library; a delta handle refuses a step without a frame mirror; a different mirror pointer triggers a full refresh;
+    cw_host_load_state injects reference-style states."""
+    import ctypes as C
+    from gym_craftingworld_b200 import _lib
+    lib = _lib.load()
+    N, size, seed = 600, 9, 5
+    cfg = cw.make_config(size=(size, size), max_steps=11)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.RandomState(8)
+    for flags in (_lib.F_AUTO_RESET, _lib.F_AUTO_RESET | _lib.F_DELTA_TRANSPORT):
+        ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=11), N, seed=seed)
+        h = C.c_void_p()
+        _lib.check(lib.cw_host_create(C.byref(cfg), N, 0, C.c_uint64(seed), C.c_uint64(0), flags, C.byref(h)))
+        delta = bool(flags & _lib.F_DELTA_TRANSPORT)
+        frames = np.zeros((N, 4 * size, 4 * size, 3), np.uint8)
+        _lib.check(lib.cw_host_reset(h, p(frames), None))
+        ob.reset(); o_obs = ob.render()
+        assert np.array_equal(frames, o_obs)
+        for k in range(25):
+            a = rng.randint(0, 6, N).astype(np.uint8).copy()      # fresh pageable arrays every call
+            rew, dn = np.zeros(N, np.int32), np.zeros(N, np.uint8)
+            if delta and k == 10:
+                frames = np.zeros_like(frames)                     # a NEW mirror: the library must refresh it in full
+            if delta and k == 5:
+                assert lib.cw_host_step(h, p(a), p(rew), p(dn), None) == -1   # CW_E_BADCONFIG
+            _lib.check(lib.cw_host_step(h, p(a), p(rew), p(dn), p(frames) if (delta or k % 2) else None))
+            o_rew, o_dn = ob.step_full(a, auto_reset=True, obs=o_obs)
+            assert np.array_equal(rew, o_rew) and np.array_equal(dn, o_dn), (flags, k)
+            if delta or k % 2:
+                assert np.array_equal(frames, o_obs), (flags, k)
+        # inject: every world gets world 0's grid / agent, step counters staggered
+        g = np.repeat(ob.grid[:1], N, 0); ag = np.repeat(ob.agent[:1], N, 0); gl = np.repeat(ob.goal[:1], N, 0)
+        t = (np.arange(N) % 11).astype(np.int32)
+        _lib.check(lib.cw_host_load_state(h, p(g), p(ag), p(gl), p(t), p(frames)))
+        ob.grid[:] = g; ob.init_grid[:] = g; ob.agent[:] = ag; ob.goal[:] = gl; ob.t[:] = t
+        o_obs = ob.render()
+        assert np.array_equal(frames, o_obs)
+        a = rng.randint(0, 6, N).astype(np.uint8)
+        rew, dn = np.zeros(N, np.int32), np.zeros(N, np.uint8)
+        _lib.check(lib.cw_host_step(h, p(a), p(rew), p(dn), p(frames)))
+        o_rew, o_dn = ob.step_full(a, auto_reset=True, obs=o_obs)
+        assert np.array_equal(rew, o_rew) and np.array_equal(dn, o_dn) and np.array_equal(frames, o_obs)
+        _lib.check(lib.cw_host_destroy(h))
