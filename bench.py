@@ -6,14 +6,25 @@
 A "step" is one pass of the hot path over one batch of worlds: ONE fused step + auto-reset + render launch
 (cw_env_kernel) per step for the pixel workloads, one cw_step_kernel launch for the compact workload.  Worlds are
 sharded over ranks by global id with no data-path collective (weak scaling: per-GPU batch fixed); with N > 1 the
-24 x int64 episode-statistics vector is all-reduced over NCCL every 128 steps on a side stream.
+24 x int64 episode-statistics vector is snapshotted on the step stream and all-reduced over NCCL on a side stream at
+every graph-replay boundary (every 128 steps, and once per timed window when K < 128), inside the timed region.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput (actions already in HBM, frames left in HBM);
-`e2e` is the same metric through the host-buffer C entry points (cw_host_step: actions from pinned host memory in,
-reward + done back to pinned host memory every step, frames produced in HBM; `e2e.frames_to_host` also copies every
-frame to the host and is PCIe-bound); `roofline` is the fused kernel's algorithmic
-bytes per launch / its mean launch duration against the measured HBM copy bandwidth; `cpu_baseline` times the CPU
-port of the reference's env loop on this box's host cores.  `--impl reference` times only that CPU port.
+Prints ONE JSON line (rank 0):
+  value         device-resident throughput of `--workload` (default cfg2 = BASELINE.json configs[1]): exactly K steps
+                replayed from CUDA graphs, actions already in HBM, frames left in HBM, CUDA events on the launching
+                stream behind a device-side gate (host launch latency is outside the window), median of several
+                windows, max over ranks.
+  workloads     the same measurement, shorter, for the other BASELINE configs (cfg3, cfg4, cfg5), each with its own
+                roofline record.
+  closed_loop   actions of step k+1 computed ON THE DEVICE from the pixels of frame k (cw_frame_policy reads every byte).
+  e2e           the same metric through the host-buffer C entry points (HostCraftingWorldEnv -> cw_host_step) with HOST
+                arrays: `e2e.value` = frames produced in HBM for a device-side consumer, actions from / reward + done
+                back to host memory every step; `e2e.host_frames_delta` additionally keeps the frames current in HOST
+                memory; `e2e.full_frame_copy` copies every frame over PCIe.
+  roofline      the fused kernel's algorithmic bytes per launch / its mean launch duration vs the measured HBM bandwidth.
+  cpu_baseline  the reference's own CraftingWorldEnvRay (oracle/_ref, installed unmodified by oracle/build_ref.py) on the
+                host cores of this box, the Python port and the C port beside it.
+`--impl reference` times only the reference's CPU env loop (rank 0).
 """
 import argparse
 import json
@@ -39,7 +50,7 @@ WORKLOADS = {
     "cfg4": dict(envs=131072, size=21, obs="pixels", dense=False,
                  desc="131072 envs default grid per GPU (1M over 8), pixel obs, stats all-reduce every 128 steps"),
     "cfg5": dict(envs=16384, size=32, obs="pixels", dense=True,
-                 desc="16384 envs 32x32 grid per GPU, dense object placement, pixel obs"),
+                 desc="16384 envs 32x32 grid per GPU, dense object placement (p=0.5 per cell, kept dense: no auto-reset), pixel obs"),
 }
 
 
@@ -49,9 +60,18 @@ def algorithmic_bytes(size, obs):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU baseline: the Python port of the reference env loop (oracle/pyenv.py), one process per host core
+# CPU baselines: the reference's own env class (oracle/_ref), its Python port, the C port -- one process / thread per core
 # ---------------------------------------------------------------------------------------------------------
-def cpu_port_throughput(size, envs_per_proc, steps, warmup, procs=None):
+def reference_installed():
+    """The unmodified reference as installed by oracle/build_ref.py (bench.py never reads /root/reference)."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isfile(os.path.join(ref, "gym_craftingworld", "envs", "craftingworld_ray.py")):
+        os.environ["CW_REFERENCE"] = ref                          # first candidate of oracle/ref_shim.py
+        return True
+    return False
+
+
+def cpu_loop_throughput(size, envs_per_proc, steps, warmup, procs=None, kind="port"):
     import multiprocessing as mp
     from oracle import pyenv
     cores = sorted(os.sched_getaffinity(0))
@@ -59,7 +79,7 @@ def cpu_port_throughput(size, envs_per_proc, steps, warmup, procs=None):
     ctx = mp.get_context("fork")
     args = [(envs_per_proc, steps, warmup, (size, size), 300, 1000 + i) for i in range(procs)]
     with ctx.Pool(procs) as pool:
-        res = pool.map(pyenv.run_worker, args)
+        res = pool.map(pyenv.run_worker_reference if kind == "reference" else pyenv.run_worker, args)
     total = sum(n for n, _ in res)
     slowest = max(dt for _, dt in res)
     return total / slowest, procs, total
@@ -82,11 +102,23 @@ def cpu_c_port_throughput(size, envs, steps, render_mode, threads):
 
 def cpu_baseline_block(size, quick=False):
     cores = len(os.sched_getaffinity(0))
+    out = {}
+    if reference_installed():
+        steps = 400 if quick else 1500
+        v, procs, total = cpu_loop_throughput(size, 16, steps, 50, kind="reference")
+        out = {"value": v, "unit": UNIT, "cores": procs, "kind": "reference",
+               "sample": f"{procs} processes x 16 worlds x {steps} steps ({total} env-steps) of the UNMODIFIED reference "
+                         f"CraftingWorldEnvRay(size=({size},{size})) env loop (step, reset on done; nine-skill random tasks), "
+                         "imported from oracle/_ref under the gym/matplotlib import shim"}
     steps = 1500 if quick else 6000
-    v, procs, total = cpu_port_throughput(size, 16, steps, 100)
-    out = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
-           "sample": f"{procs} processes x 16 worlds x {steps} steps ({total} env-steps) of the {size}x{size} nine-skill "
-                     f"env loop, Python/NumPy port of the reference (oracle/pyenv.py: incremental render_edit, reset on done)"}
+    v, procs, total = cpu_loop_throughput(size, 16, steps, 100, kind="port")
+    port = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": f"{procs} processes x 16 worlds x {steps} steps ({total} env-steps) of the {size}x{size} nine-skill "
+                      f"env loop, Python/NumPy port of the reference (oracle/pyenv.py: incremental render_edit, reset on done)"}
+    if out:
+        out["port"] = port
+    else:
+        out = port
     try:
         k = 40 if quick else 150
         out["c_port"] = {
@@ -100,53 +132,70 @@ def cpu_baseline_block(size, quick=False):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# clocks
+# clocks: NVML polled from a thread (~1 ms period) so that even a sub-millisecond timed region has samples inside
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index):
-        self.samples, self.proc = [], None
+    def __init__(self, local_rank):
+        self.samples, self.stop_flag, self.thread, self.sm_max, self.src = [], False, None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = self._handle(local_rank)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.src = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:  # noqa: BLE001
-            self.proc = None
+            self.nv = None
+        deadline = time.perf_counter() + 2.0                      # do not start measuring before the first sample exists
+        while self.nv is not None and not self.samples and time.perf_counter() < deadline:
+            time.sleep(0.001)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.perf_counter(), line.strip()))
+    def _handle(self, local_rank):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            tok = vis.split(",")[local_rank].strip()
+            if tok.startswith("GPU-"):
+                return self.nv.nvmlDeviceGetHandleByUUID(tok)
+            idx = int(tok)
+        return self.nv.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), float(sm), int(rs)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.0005)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        self.stop_flag = True
 
     def summary(self, t0, t1, t_load0):
-        def parse(rows):
-            sm, mx, reasons = [], 0.0, set()
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for _, line in rows:
-                p = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(p[0])); mx = max(mx, float(p[1]))
-                except (ValueError, IndexError):
-                    continue
-                for nm, val in zip(names, p[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-            return sm, mx, sorted(reasons)
-        timed = [s for s in self.samples if t0 <= s[0] <= t1]
+        rows = [s for s in self.samples if t0 <= s[0] <= t1]
         window = "timed region"
-        if len(timed) < 3:
-            timed = [s for s in self.samples if t_load0 <= s[0] <= t1 + 0.3]
+        if len(rows) < 3:
+            rows = [s for s in self.samples if t_load0 <= s[0] <= t1 + 0.05]
             window = "warm-up + timed region (timed region shorter than 3 samples)"
-        sm, mx, reasons = parse(timed)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "window": window}
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "window": window, "source": self.src}
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        reasons = sorted(nm for nm, b in self.REASONS.items() if bits & b)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm),
+                "samples_in_timed_region": len([s for s in self.samples if t0 <= s[0] <= t1]), "window": window, "source": self.src}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -185,286 +234,411 @@ def dense_worlds(env, torch, seed):
                    torch.zeros(N).numpy(), desired.cpu().numpy())
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Per-process measurement context: device, ranks, stream, barrier, timing of exactly K steps."""
 
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        """element-wise MAX over ranks of a list of floats; also returns every rank's list (rank-major)"""
+        torch = self.torch
+        t = torch.tensor(values, device=self.dev, dtype=torch.float64)
+        if self.world == 1:
+            return list(values), [list(values)]
+        allr = [torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(allr, t)
+        stack = torch.stack(allr)
+        return stack.max(dim=0).values.tolist(), stack.tolist()
+
+    def time_steps(self, enqueue, K, windows=None):
+        """Device time of exactly K steps, `windows` times.  `enqueue()` puts the K steps on self.stream.  Each window is
+        bracketed by barrier + synchronize; a ~0.3 ms device-side gate in front of the first event keeps the host's launch
+        latency out of the CUDA-event window (everything is queued before the GPU reaches the start event)."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            enqueue()                                             # untimed: also tells how long a window is
+            torch.cuda.synchronize()
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream); enqueue(); e1.record(self.stream)
+            torch.cuda.synchronize()
+            est = e0.elapsed_time(e1)
+            if windows is None:
+                windows = 5 if est < 400 else (3 if est < 3000 else 1)
+            ms = []
+            w0 = time.perf_counter()
+            for _ in range(windows):
+                self.barrier()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda._sleep(int(0.3e-3 * 1.9e9))           # the gate
+                ev0.record(self.stream)
+                enqueue()
+                ev1.record(self.stream)
+                torch.cuda.synchronize()
+                ms.append(ev0.elapsed_time(ev1))
+            w1 = time.perf_counter()
+            self.barrier()
+        mx, per_rank = self.max_over_ranks(ms)                    # per window: MAX over ranks
+        order = sorted(range(len(mx)), key=lambda i: mx[i])
+        mid = order[len(order) // 2]
+        ranks_mid = sorted(r[mid] for r in per_rank)
+        return {"ms": mx[mid], "windows_ms": mx, "rank_ms": {"min": ranks_mid[0], "median": ranks_mid[len(ranks_mid) // 2], "max": ranks_mid[-1]},
+                "t0": w0, "t1": w1}
+
+
+def stagger(env, torch, seed):
+    """Spread the episode clocks uniformly over [0, max_steps): every step then sees the steady-state share of time-outs and
+    re-seeds (N / max_steps worlds) instead of a synchronised storm every max_steps steps."""
+    g = torch.Generator(device=env.device).manual_seed(seed)
+    env.t.copy_(torch.randint(0, env.MAX_STEPS, (env.num_envs,), generator=g, device=env.device, dtype=torch.int32))
+
+
+def pixel_or_compact_leg(cx, name, K, W_, main):
+    """One BASELINE workload on this rank's GPU: returns the record (value, roofline, ...) -- the full set of legs when it is
+    the main workload, the chained + independent-launch legs otherwise."""
     import gym_craftingworld_b200 as cw
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = dict(WORKLOADS[args.workload])
-    if args.envs:
+    torch, args = cx.torch, cx.args
+    wl = dict(WORKLOADS[name])
+    if args.envs and main:
         wl["envs"] = args.envs
-    K, W_ = args.steps, max(args.warmup, 3)
-
-    cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:                  # before CUDA is initialised (fork-safe)
-        cpu_base = cpu_baseline_block(wl["size"], quick=args.quick)
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    N, size = wl["envs"], wl["size"]
-    pixels = wl["obs"] == "pixels"
+    N, size, pixels = wl["envs"], wl["size"], wl["obs"] == "pixels"
     frame_bytes = 48 * size * size
     ring = 1
-    if pixels:                                                   # rotate frame buffers so the ring exceeds the 126 MB L2
+    if pixels:                                                    # rotate frame buffers so the ring exceeds the 126 MB L2
         while N * frame_bytes * ring < 300e6 and ring < 64:
             ring *= 2
-        if not args.no_chain:
-            ring = max(ring, 2)                                  # chained launches overlap step i+1 with the stores of step i
-        if args.ring:
+        ring = max(ring, 2)                                       # chained launches overlap step i+1 with the stores of step i
+        if args.ring and main:
             ring = args.ring
-    env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=dev, auto_reset=True, obs_mode=wl["obs"],
-                                     env_id_base=rank * N, obs_buffers=ring, goal_images=not args.no_goal_images,
+    auto_reset = not wl["dense"]                                  # cfg5 stays dense: a re-seed would replace a dense world by a 9-object one
+    env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=cx.dev, auto_reset=auto_reset, obs_mode=wl["obs"],
+                                     env_id_base=cx.rank * N, obs_buffers=ring, goal_images=not args.no_goal_images,
                                      max_steps=args.max_steps, collect_stats=not args.no_stats)
     env.reset()
     if wl["dense"]:
-        dense_worlds(env, torch, 99 + rank)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    tape = torch.randint(0, 6, (TAPE, N), generator=gen, device=dev, dtype=torch.uint8)
-    reducer = cw.StatsReducer(env.stats_raw, every=TAPE, inline=os.environ.get("CW_STATS_INLINE", "0") == "1") if world > 1 else None
+        dense_worlds(env, torch, 99 + cx.rank)
+    else:
+        stagger(env, torch, 7 + cx.rank)
+    gen = torch.Generator(device=cx.dev).manual_seed(1234 + cx.rank)
+    tape = torch.randint(0, 6, (TAPE, N), generator=gen, device=cx.dev, dtype=torch.uint8)
+    reducer = cw.StatsReducer(env, every=TAPE, inline=os.environ.get("CW_STATS_INLINE", "0") == "1") if cx.world > 1 else None
+    stream = cx.stream
+    peak, peak_src = measured_peak()
+    B = algorithmic_bytes(size, wl["obs"])
+    rec = {"workload": f"{name}: {wl['desc']}", "envs_per_gpu": N, "grid": f"{size}x{size}", "obs": wl["obs"], "steps": K}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    stream = torch.cuda.Stream(device=dev)
-    t_load0 = time.perf_counter()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     with torch.cuda.stream(stream):
-        for k in range(W_):                                      # eager warm-up (also warms the launch path)
+        for k in range(W_):                                       # eager warm-up (also warms the launch path)
             env.step(tape[k % TAPE])
         torch.cuda.synchronize()
-
         chain = pixels and not args.no_chain
         if chain:
-            env.step(tape[0], chain_pos=0)                       # warm the chained launch path outside the capture
+            env.step(tape[0], chain_pos=0)                        # warm the chained launch path outside the capture
 
-        def capture(nsteps, chained):
+        def capture(nsteps, body):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
                 for k in range(nsteps):
-                    env.step(tape[k], chain_pos=k if chained else None)
+                    body(k)
             return g
 
-        def timed(chained):
-            """exactly K steps replayed from graphs of TAPE steps; device time between two events, max over ranks"""
+        def graph_runner(body):
+            """exactly K steps as replays of graphs of <= TAPE steps; the statistics reduction fires at EVERY replay boundary
+            (snapshot on this stream, NCCL on a side stream) and the window only closes once it has finished"""
             n_full, rem = divmod(K, TAPE)
-            g_full = capture(TAPE, chained) if n_full else None
-            g_rem = capture(rem, chained) if rem else None
-            for g in (g_full, g_rem):                            # one untimed replay each (extra warm-up)
-                if g is not None:
-                    g.replay()
-            torch.cuda.synchronize()
-            barrier()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            w0 = time.perf_counter()
-            ev0.record(stream)
-            for _ in range(n_full):
-                g_full.replay()
+            g_full = capture(TAPE, body) if n_full else None
+            g_rem = capture(rem, body) if rem else None
+
+            def enqueue():
+                for _ in range(n_full):
+                    g_full.replay()
+                    if reducer is not None:
+                        reducer.reduce_async()
+                if g_rem is not None:
+                    g_rem.replay()
+                    if reducer is not None:
+                        reducer.reduce_async()
                 if reducer is not None:
-                    reducer.reduce_async()                       # every 128 steps, on a side stream
-            if g_rem is not None:
-                g_rem.replay()
-            ev1.record(stream)
-            torch.cuda.synchronize()
-            w1 = time.perf_counter()
-            barrier()
+                    reducer.wait()                                # `stream` waits for the side stream: the all-reduce is inside the window
+            return enqueue
+
+    res = cx.time_steps(graph_runner(lambda k: env.step(tape[k], chain_pos=k if chain else None)), K)
+    ms = res["ms"]
+    rec.update(value=N * cx.world * K / (ms / 1e3), unit=UNIT, ms_per_step=ms / K, windows_ms=res["windows_ms"], rank_ms=res["rank_ms"],
+               gpu_launches=K, t0=res["t0"], t1=res["t1"],
+               launch=(f"CUDA graphs of <= {TAPE} steps, one launch per step"
+                       + ("; launches chained by per-group dataflow (cw_step_render_chained: open-loop action tape, step i+1 overlaps "
+                          "the draining frame stores of step i; results identical)" if chain else "")),
+               l2=(f"frames written round-robin into {ring} buffers = {ring * N * frame_bytes / 1e6:.0f} MB > 126 MB L2 (inputs larger than "
+                   "L2; no flush needed)") if pixels else "state 65536 x ~0.9 KB; step kernel is latency bound",
+               episodes=("kept dense: auto-reset off, worlds step past done as upstream allows" if wl["dense"] else
+                         "episode clocks staggered uniformly over [0, max_steps): steady-state share of time-outs / re-seeds in every step"),
+               stats_allreduce=(f"{reducer.reductions} NCCL all-reduces of the 16x24 int64 statistics issued so far (one per graph replay), "
+                                "inside the timed windows") if reducer is not None else None)
+    launch_s = ms / 1e3 / K
+    achieved = B * N / launch_s / 1e9
+    if pixels:
+        rec["roofline"] = {"bound": "hbm", "kernel": "cw_env_kernel<V_CHAINED>" if chain else "cw_env_kernel<V_PLAIN>", "achieved": achieved,
+                           "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(name),
+                           "algorithmic_bytes_per_env_step": B, "units_per_launch": N, "launch_us": launch_s * 1e6, "peak_source": peak_src}
+    else:
+        rec["roofline"] = {"bound": "latency/issue (reported, not an HBM roofline: 32 algorithmic bytes per env-step)", "kernel": "cw_step_kernel<false>",
+                           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(name),
+                           "algorithmic_bytes_per_env_step": B, "units_per_launch": N, "launch_us": launch_s * 1e6, "peak_source": peak_src}
+
+    if main and pixels and K < 1280 and not args.no_steady:
+        # K steps from an idle GPU to a drained one pay one pipeline fill + drain (~1 step of 20); the same launches over a long
+        # window show the steady state the kernel sustains.  Reported beside `value`, never instead of it.
+        Ks = 2560
+        with torch.cuda.stream(stream):
+            g_ss = capture(TAPE, lambda k: env.step(tape[k], chain_pos=k if chain else None))
+
+        def run_ss():
+            for _ in range(Ks // TAPE):
+                g_ss.replay()
+                if reducer is not None:
+                    reducer.reduce_async()
             if reducer is not None:
                 reducer.wait()
-            t_ms = ev0.elapsed_time(ev1)
-            if world > 1:
-                tmax = torch.tensor([t_ms], device=dev)
-                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-                t_ms = float(tmax.item())
-            return t_ms, w0, w1
+        rs = cx.time_steps(run_ss, Ks, windows=3)
+        rec["steady_state"] = {"steps": Ks, "value": N * cx.world * Ks / (rs["ms"] / 1e3), "unit": UNIT, "ms_per_step": rs["ms"] / Ks,
+                               "roofline_frac": B * N / (rs["ms"] / 1e3 / Ks) / 1e9 / peak, "windows_ms": rs["windows_ms"],
+                               "note": f"the same chained launches, {Ks} steps per window (20 graph replays): the K-step window of `value` "
+                                       "runs from an idle GPU to a drained one, this one amortises that fill + drain"}
 
-        ms_unchained = None
-        if chain and not args.no_unchained:                      # the same K steps as independent launches, for comparison
-            ms_unchained, _, _ = timed(False)
-        ms, t0, t1 = timed(chain)
-    stats_local = env.episode_stats()
-    if sampler:
-        sampler.stop()                                           # the clock record covers warm-up + the timed region of `value`; the
-                                                                 # nvidia-smi poller must not compete with the host threads of the e2e legs
+    if chain and not args.no_unchained:                           # the same K steps as independent launches, for comparison
+        with torch.cuda.stream(stream):
+            run = graph_runner(lambda k: env.step(tape[k]))
+        r2 = cx.time_steps(run, K)
+        rec["unchained"] = {"value": N * cx.world * K / (r2["ms"] / 1e3), "unit": UNIT, "ms_per_step": r2["ms"] / K,
+                            "roofline_frac": B * N / (r2["ms"] / 1e3 / K) / 1e9 / peak,
+                            "note": "the same K steps as independent (whole-grid dependent, PDL) launches"}
+
+    if pixels and not args.no_closed_loop:
+        # closed loop with a REAL device consumer: between two steps a kernel reads every byte of every frame and derives the
+        # next actions from the pixels (cw_frame_policy), so step k+1 depends on frame k.  Bytes per step: the frames are
+        # written once and read once.
+        abuf = torch.zeros(N, dtype=torch.uint8, device=cx.dev)
+
+        def body(k):
+            env.frame_policy(out=abuf)
+            env.step(abuf)
+        with torch.cuda.stream(stream):
+            body(0)
+            run = graph_runner(body)
+        r3 = cx.time_steps(run, K)
+        Bc = B + frame_bytes + 1
+        ach = Bc * N / (r3["ms"] / 1e3 / K) / 1e9
+        rec["closed_loop"] = {"value": N * cx.world * K / (r3["ms"] / 1e3), "unit": UNIT, "ms_per_step": r3["ms"] / K, "gpu_launches": 2 * K,
+                              "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                           "algorithmic_bytes_per_env_step": Bc},
+                              "note": "per step: cw_frame_policy (a device consumer that reads every frame byte and computes the next "
+                                      "action from the pixels) + one independent fused launch; the frames are written AND read"}
+    rec["episode_stats_rank0"] = {k: v for k, v in env.episode_stats().items() if k in ("episodes", "successes", "mean_return", "mean_length")}
 
     # ---- compact workload: the same open-loop tape as ONE launch per 128 steps (cw_rollout) -------------------------
-    rollout = None
     if not pixels:
-        with torch.cuda.stream(stream):
-            for _ in range(3):
-                env.rollout(tape, return_trace=False)
-            torch.cuda.synchronize()
-            barrier()
-            reps = max(1, min(K, 12800) // TAPE)
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(stream)
+        reps = max(1, K // TAPE)
+
+        def run():
             for _ in range(reps):
                 env.rollout(tape, return_trace=False)
-            ev1.record(stream)
-            torch.cuda.synchronize()
-            barrier()
-        rms = ev0.elapsed_time(ev1)
-        if world > 1:
-            tmax = torch.tensor([rms], device=dev)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            rms = float(tmax.item())
-        rollout = {"value": N * world * reps * TAPE / (rms / 1e3), "unit": UNIT, "steps": reps * TAPE, "gpu_launches": reps,
-                   "note": f"cw_rollout: {TAPE} steps of the same tape per launch, state in registers across the steps (open loop only)"}
+        r4 = cx.time_steps(run, reps * TAPE)
+        rec["rollout"] = {"value": N * cx.world * reps * TAPE / (r4["ms"] / 1e3), "unit": UNIT, "steps": reps * TAPE, "gpu_launches": reps,
+                          "ms_per_step": r4["ms"] / (reps * TAPE),
+                          "note": f"cw_rollout: {TAPE} steps of the same tape per launch, state in registers across the steps (open loop only)"}
 
     # ---- the same workload with INCREMENTAL rendering (the reference's render_edit, cw_step_render_edit) --------------
-    incremental = None
-    if pixels and not args.no_incremental:
+    if pixels and main and not args.no_incremental and auto_reset:
         del env
         torch.cuda.empty_cache()
-        ienv = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=dev, auto_reset=True, env_id_base=rank * N,
+        ienv = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=cx.dev, auto_reset=True, env_id_base=cx.rank * N,
                                           goal_images=not args.no_goal_images, max_steps=args.max_steps,
                                           collect_stats=not args.no_stats, render="incremental")
         ienv.reset()
-        if wl["dense"]:
-            dense_worlds(ienv, torch, 99 + rank)
+        stagger(ienv, torch, 7 + cx.rank)
+        reducer = None
         with torch.cuda.stream(stream):
             for k in range(3):
                 ienv.step(tape[k])
-            gi = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gi, stream=stream):
-                for k in range(TAPE):
-                    ienv.step(tape[k])
-            gi.replay()
-            torch.cuda.synchronize()
-            barrier()
-            reps = max(1, min(K, 12800) // TAPE)
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(stream)
-            for _ in range(reps):
-                gi.replay()
-            ev1.record(stream)
-            torch.cuda.synchronize()
-            barrier()
-        ims = ev0.elapsed_time(ev1)
-        if world > 1:
-            tmax = torch.tensor([ims], device=dev)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            ims = float(tmax.item())
-        incremental = {"value": N * world * reps * TAPE / (ims / 1e3), "unit": UNIT, "steps": reps * TAPE, "ms_per_step": ims / (reps * TAPE),
-                       "gpu_launches": 2 * reps * TAPE,
-                       "note": "render='incremental' (cw_step_render_edit): the persistent frame buffer in HBM is kept current by "
-                               "rewriting only the <= 2 cells a step changes (what the reference's step does, ray.py:358, 522-557) "
-                               "plus full frames for re-seeded worlds; identical pixels, ~100x fewer bytes, so NOT comparable with "
-                               "the roofline of the full-expansion path that `value` measures"}
+            n_full, rem = divmod(K, TAPE)
+            gi = capture(TAPE if n_full else rem, lambda k: ienv.step(tape[k]))
+        per = TAPE if n_full else rem
+        reps = max(1, K // per)
+        r5 = cx.time_steps(lambda: [gi.replay() for _ in range(reps)], reps * per)
+        rec["incremental_render"] = {"value": N * cx.world * reps * per / (r5["ms"] / 1e3), "unit": UNIT, "steps": reps * per,
+                                     "ms_per_step": r5["ms"] / (reps * per), "gpu_launches": 2 * reps * per,
+                                     "note": "render='incremental' (cw_step_render_edit): the persistent frame buffer in HBM is kept current by "
+                                             "rewriting only the <= 2 cells a step changes (what the reference's step does, ray.py:358, 522-557) "
+                                             "plus full frames for re-seeded worlds; identical pixels, ~100x fewer bytes, so NOT comparable with "
+                                             "the roofline of the full-expansion path that `value` measures"}
         del ienv
+    torch.cuda.empty_cache()
+    return rec, tape
 
-    # ---- end to end through the host-buffer C entry points --------------------------------------------------
-    e2e = {}
-    if pixels and not args.no_e2e:
-        e_steps = max(10, min(K, 1000 if not args.quick else 30))
-        if N * frame_bytes > 1.5e9:
-            e_steps = min(e_steps, 100)
-        res = {}
-        for variant in ("device", "delta", "frames"):
-            henv = cw.HostCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=local_rank, env_id_base=rank * N,
-                                           return_frames=variant != "device", transport="delta" if variant == "delta" else "frames")
-            henv.reset()
-            acts = tape.cpu().numpy()
-            n_steps = e_steps if variant != "frames" else max(10, e_steps // 10)
-            for k in range(20 if variant != "frames" else 3):  # untimed: page-faults of the mirrors, worker threads hot
-                henv.step(acts[k])
-            barrier()
-            h0 = time.perf_counter()
-            for k in range(n_steps):
-                henv.step(acts[k % TAPE])
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - h0
-            if world > 1:
-                tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                dt = float(tt.item())
-            res[variant] = {"value": N * world * n_steps / dt, "unit": UNIT, "h2d_bytes_per_step": henv.h2d_bytes_per_step,
-                            "d2h_bytes_per_step": henv.d2h_bytes_per_step, "steps": n_steps}
-            henv.close()
-            barrier()
-        e2e = dict(res["delta"])
-        e2e["api"] = ("HostCraftingWorldEnv(transport='delta').step -> cw_host_step: every step the actions come from host memory and "
-                      "reward, done AND the current pixel frames are in host memory when the call returns. A thread-per-world kernel "
-                      "writes a 16-byte sequence-tagged delta record per world (72 B more for a re-seeded world) into mapped pinned "
-                      "memory; the library's worker threads poll the records while the kernel runs (no stream sync) and patch the <=2 "
-                      "changed cells of each world in the caller's frame buffer -- what the reference's render_edit does (bit-identical "
-                      "to a full device render + copy; tests/test_gpu_parity.py::test_host_env_delta_transport_matches_oracle)")
-        e2e["frames_left_on_device"] = dict(res["device"], note="same call with obs_host=NULL: frames are rendered into HBM by the "
-                                            "fused kernel for a device-side consumer; only reward/done return to the host")
-        e2e["full_frame_copy"] = dict(res["frames"], note="same call with transport='frames': every rendered frame copied over PCIe "
-                                      "(sliced, two streams); PCIe-bound at ~52 GB/s")
 
-    if rank == 0:
-        secs = ms / 1e3
-        value = N * world * K / secs
-        peak, peak_src = measured_peak()
-        B = algorithmic_bytes(size, wl["obs"])
-        launch_s = secs / K
-        achieved = B * N / launch_s / 1e9
+def e2e_legs(cx, name, K, tape):
+    """The metric through the host-buffer C entry points (HostCraftingWorldEnv -> cw_host_step), host arrays in and out, wall clock,
+    MAX over ranks."""
+    import numpy as np
+    import gym_craftingworld_b200 as cw
+    torch, args = cx.torch, cx.args
+    wl = WORKLOADS[name]
+    N, size = (args.envs or wl["envs"]), wl["size"]
+    frame_bytes = 48 * size * size
+    e_steps = max(K, 1000 if not args.quick else 30)
+    e_steps = min(e_steps, 4000)
+    if N * frame_bytes > 1.5e9:
+        e_steps = min(e_steps, 200)
+    acts = tape.cpu().numpy()
+    res = {}
+
+    def timed(fn, n_calls, steps_per_call):
+        cx.barrier()
+        h0 = time.perf_counter()
+        for k in range(n_calls):
+            fn(k)
+        henv.sync()                                               # device-consumer legs: the frames of the last step are complete
+        dt = time.perf_counter() - h0
+        mx, _ = cx.max_over_ranks([dt])
+        return N * cx.world * n_calls * steps_per_call / mx[0]
+
+    for variant in ("device", "delta", "frames"):
+        henv = cw.HostCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=cx.local_rank, env_id_base=cx.rank * N,
+                                       return_frames=variant != "device", transport="delta" if variant == "delta" else "frames",
+                                       max_steps=args.max_steps)
+        henv.reset()
+        henv.load_state(t=np.random.RandomState(11 + cx.rank).randint(0, args.max_steps, N))   # staggered episode clocks (as above)
+        n_steps = e_steps if variant != "frames" else max(10, e_steps // 50)
+        for k in range(20 if variant != "frames" else 3):         # untimed: page-faults of the mirrors, worker threads hot
+            henv.step(acts[k])
+        v = timed(lambda k: henv.step(acts[k % TAPE]), n_steps, 1)
+        res[variant] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": henv.h2d_bytes_per_step, "d2h_bytes_per_step": henv.d2h_bytes_per_step,
+                        "steps": n_steps}
+        if variant == "device":                                   # the same transport, 128 steps of an open-loop tape per library call
+            calls = max(1, min(e_steps // TAPE, 16))
+            henv.step_many(acts)
+            res["device_many"] = {"value": timed(lambda k: henv.step_many(acts), calls, TAPE), "unit": UNIT, "steps": calls * TAPE,
+                                  "h2d_bytes_per_step": N, "d2h_bytes_per_step": N}
+        henv.close()
+        cx.barrier()
+    e2e = dict(res["device"])
+    e2e["api"] = ("HostCraftingWorldEnv(return_frames=False).step -> cw_host_step(obs_host=NULL): every step the actions come from pinned HOST "
+                  "memory and reward + done are back in HOST memory when the call returns (one status byte per world through mapped pinned "
+                  "memory, no stream synchronisation); the pixel frames are produced in HBM by the fused step+reset+render kernel (chained "
+                  "launches, two-to-four rotating frame buffers) for a device-side consumer -- the call a GPU policy loop makes. "
+                  "tests/test_gpu_parity.py::test_host_env_device_consumer_matches_oracle")
+    e2e["step_many_128"] = dict(res["device_many"], note="cw_host_step_many: 128 steps of an open-loop tape per library call (K chained launches, "
+                                "reward/done rows unpacked as they land)")
+    e2e["host_frames_delta"] = dict(res["delta"], note="transport='delta': additionally the CURRENT pixel frames are in HOST memory after every call "
+                                    "(16-byte pre-digested records + host-side render_edit by a worker pool; bit-identical to a device render + copy). "
+                                    "Bound by the host cores' memory system (~50 ns per world-step per core, tools/patch_bench.cpp), not by the GPU")
+    e2e["full_frame_copy"] = dict(res["frames"], note="transport='frames': every rendered frame copied over PCIe (sliced, two streams); PCIe-bound at ~52 GB/s")
+    return e2e
+
+
+def run_ours(args):
+    K, W_ = args.steps, max(args.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:                  # before CUDA is initialised (fork-safe)
+        cpu_base = cpu_baseline_block(WORKLOADS[args.workload]["size"], quick=args.quick)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None   # before any GPU work; waits for its first sample
+    t_load0 = time.perf_counter()
+    cx = Ctx(args)
+    main_rec, tape = pixel_or_compact_leg(cx, args.workload, K, W_, True)
+    pixels = WORKLOADS[args.workload]["obs"] == "pixels"
+    others = {}
+    if not args.only:
+        k_sub = max(3, min(K, 256))
+        for name in ("cfg3", "cfg4", "cfg5"):
+            if name == args.workload:
+                continue
+            rec, _ = pixel_or_compact_leg(cx, name, k_sub, 3, False)
+            for key in ("t0", "t1"):
+                rec.pop(key, None)
+            others[name] = rec
+    if sampler:
+        sampler.stop()                                           # the nvidia poller must not compete with the host threads of the e2e legs
+    e2e = e2e_legs(cx, args.workload, K, tape) if (pixels and not args.no_e2e) else None
+
+    if cx.rank == 0:
+        t0, t1 = main_rec.pop("t0"), main_rec.pop("t1")
+        roof = main_rec.pop("roofline")
+        roof["note"] = ("launch duration = CUDA-event time of the timed region / launches (includes inter-kernel gaps). peak is the measured COPY "
+                        "bandwidth (read+write mix); this kernel is a ~98% write stream, which does not pay a copy's read/write turnarounds, so "
+                        "frac can slightly exceed 1. traffic = dram__bytes_read+write per launch from ncu (profiles/traffic.json)")
         line = {
-            "metric": METRIC if pixels else "env-steps/sec compact obs (step kernel only)", "value": value, "unit": UNIT,
-            "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC if pixels else "env-steps/sec compact obs (step kernel only)", "value": main_rec["value"], "unit": UNIT,
+            "n_gpus": cx.world, "steps": K, "warmup": W_, "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']}", "envs_per_gpu": N, "grid": f"{size}x{size}", "obs": wl["obs"],
+            "config": {"workload": main_rec["workload"], "envs_per_gpu": main_rec["envs_per_gpu"], "grid": main_rec["grid"], "obs": main_rec["obs"],
                        "actions": "uniform iid over 6 actions, pre-generated uint8[128,N] tape on device, cycled",
-                       "launch": (f"CUDA graphs of {TAPE} steps, one fused launch per step"
-                                  + ("; launches chained by per-group dataflow (cw_step_render_chained: open-loop action tape, step i+1 "
-                                     "overlaps the draining frame stores of step i; results identical)" if chain else "")),
-                       "l2": (f"frames written round-robin into {ring} buffers = {ring * N * frame_bytes / 1e6:.0f} MB > 126 MB L2 "
-                              "(inputs larger than L2; no flush needed)") if pixels else "state 65536 x ~0.9 KB; step kernel is latency bound",
-                       "parallelism": f"dp{world} (worlds sharded by global id, no data-path collective)"},
+                       "launch": main_rec["launch"], "l2": main_rec["l2"], "episodes": main_rec["episodes"],
+                       "timing": "exactly K steps between two CUDA events on the launching stream, behind a ~0.3 ms device-side gate so that every "
+                                 "launch is queued before the start event; median of len(windows_ms) such windows, each MAX over ranks",
+                       "parallelism": f"dp{cx.world} (worlds sharded by global id, no data-path collective)"},
+            "windows_ms": main_rec["windows_ms"], "rank_ms": main_rec["rank_ms"], "stats_allreduce": main_rec["stats_allreduce"],
             "clocks": sampler.summary(t0, t1, t_load0) if sampler else None,
-            "gpu_launches": K,
-            "unchained": ({"value": N * world * K / (ms_unchained / 1e3), "unit": UNIT, "ms_per_step": ms_unchained / K,
-                           "roofline_frac": B * N / (ms_unchained / 1e3 / K) / 1e9 / peak,
-                           "note": "the same K steps as independent (whole-grid dependent, PDL) launches: what a closed loop "
-                                   "with a policy between the steps can use"} if ms_unchained else None),
-            "incremental_render": incremental,
-            "rollout": rollout,
-            "e2e": e2e or None,
-            "roofline": {"bound": "hbm", "kernel": ("cw_env_kernel<V_CHAINED>" if chain else "cw_env_kernel<V_PLAIN>") if pixels else "cw_step_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
-                         "algorithmic_bytes_per_env_step": B, "units_per_launch": N, "launch_us": launch_s * 1e6,
-                         "peak_source": peak_src,
-                         "note": "launch duration = CUDA-event time of the timed region / launches (includes inter-kernel gaps). "
-                                 "peak is the measured COPY bandwidth (read+write mix); this kernel is a ~98% write stream, which does "
-                                 "not pay a copy's read/write turnarounds, so frac can slightly exceed 1. traffic (ncu, one isolated "
-                                 "launch) is below the algorithmic bytes at 4096 worlds because the 126 MB L2 writes part of the frame "
-                                 "back after the profiled launch"},
+            "gpu_launches": main_rec["gpu_launches"],
+            "steady_state": main_rec.get("steady_state"),
+            "unchained": main_rec.get("unchained"), "closed_loop": main_rec.get("closed_loop"),
+            "incremental_render": main_rec.get("incremental_render"), "rollout": main_rec.get("rollout"),
+            "workloads": others or None,
+            "e2e": e2e,
+            "roofline": roof,
             "cpu_baseline": cpu_base,
-            "episode_stats_rank0": {k: stats_local[k] for k in ("episodes", "successes", "mean_return", "mean_length")},
+            "episode_stats_rank0": main_rec["episode_stats_rank0"],
         }
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 def run_reference(args):
-    """The reference arm: the CPU port of the reference env loop on all host cores (rank 0 only)."""
+    """The reference arm: the reference's OWN CraftingWorldEnvRay (oracle/_ref, unmodified) on all host cores of the box, rank 0
+    only; falls back to the Python port when the install is absent."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     wl = WORKLOADS[args.workload]
     K, W_ = args.steps, max(args.warmup, 3)
     cores = len(os.sched_getaffinity(0))
+    kind = "reference" if reference_installed() else "port"
     # a "step" steps every world of the bounded sample once: `per_proc` worlds per process, sized from a short
     # calibration so that K steps take roughly 15 s of wall clock (never more than a few minutes)
-    rate, _, _ = cpu_port_throughput(wl["size"], 8, 200, 20, procs=cores)
-    per_proc = int(max(1, min(2048, rate / cores * 15.0 / max(K, 1))))
-    value, procs, total = cpu_port_throughput(wl["size"], per_proc, K, W_, procs=cores)
+    rate, _, _ = cpu_loop_throughput(wl["size"], 4, 100, 10, procs=cores, kind=kind)
+    # (at most 128 worlds per process: a reference env object carries ~1 MB of int64 arrays, and with more of them per core the
+    # loop falls out of cache -- the arm should show the reference at its best)
+    per_proc = int(max(1, min(128, rate / cores * 15.0 / max(K + W_, 1))))
+    value, procs, total = cpu_loop_throughput(wl["size"], per_proc, K, W_, procs=cores, kind=kind)
+    what = ("the UNMODIFIED reference class CraftingWorldEnvRay (gym_craftingworld 0.1.9.8, installed into oracle/_ref by oracle/build_ref.py, "
+            "imported under the gym/matplotlib shim)" if kind == "reference" else
+            "Python/NumPy port of the reference (oracle/pyenv.py) -- oracle/_ref is absent on this box")
     sample = (f"{procs} processes x {per_proc} worlds, one step = every world stepped once ({procs * per_proc} env-steps), "
-              f"{wl['size']}x{wl['size']} nine-skill env loop with reset on done; Python/NumPy port of the reference "
-              "(oracle/pyenv.py) -- the reference itself cannot be imported on this box (no gym / matplotlib)")
+              f"{wl['size']}x{wl['size']} nine-skill env loop with reset on done; {what}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": K, "warmup": W_, "ms_per_step": 1e3 * procs * per_proc / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']} (bounded CPU sample)", "grid": f"{wl['size']}x{wl['size']}"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "grid": f"{wl['size']}x{wl['size']}",
+                       "sample": "bounded CPU sample of the same env config (see cpu_baseline.sample)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -494,10 +668,11 @@ def quiet_stdout() -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=25600)
-    ap.add_argument("--warmup", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=2560)
+    ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--only", action="store_true", help="measure only --workload (skip the sub-records of the other BASELINE configs)")
     ap.add_argument("--envs", type=int, default=0, help="override worlds per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--quick", action="store_true", help="shorter CPU baseline / e2e legs")
@@ -506,6 +681,8 @@ def main():
     ap.add_argument("--ring", type=int, default=0, help="override the number of rotating frame buffers")
     ap.add_argument("--no-chain", action="store_true", help="independent launches instead of chained ones")
     ap.add_argument("--no-unchained", action="store_true", help="skip the comparison leg with independent launches")
+    ap.add_argument("--no-steady", action="store_true", help="skip the long-window (steady state) leg of the main workload")
+    ap.add_argument("--no-closed-loop", action="store_true", help="skip the closed-loop leg (device consumer between the steps)")
     ap.add_argument("--no-incremental", action="store_true", help="skip the incremental-rendering leg")
     ap.add_argument("--no-stats", action="store_true", help="experiment: do not accumulate episode statistics")
     ap.add_argument("--no-goal-images", action="store_true", help="experiment: skip imagine_obs / goal + init frames")

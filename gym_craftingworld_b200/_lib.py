@@ -19,7 +19,7 @@ F_DELTA_TRANSPORT = 2
 
 # every symbol include/cw_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_step_render_chained", "cw_step_render_edit", "cw_step_delta", "cw_rollout",
-           "cw_imagine", "cw_onehot", "cw_render_alt", "cw_host_create", "cw_host_reset", "cw_host_bind_actions", "cw_host_step",
+           "cw_imagine", "cw_frame_policy", "cw_onehot", "cw_render_alt", "cw_host_create", "cw_host_reset", "cw_host_bind_actions", "cw_host_step",
            "cw_host_step_many", "cw_host_load_state", "cw_host_stats", "cw_host_device_state", "cw_host_stream", "cw_host_fetch_frames", "cw_host_sync",
            "cw_host_destroy"]
 
@@ -62,6 +62,7 @@ def _declare(lib):
         "cw_step_delta": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
         "cw_imagine": [cfgp, stp, vp, vp],
         "cw_onehot": [cfgp, vp, vp, vp, i64, vp],
+        "cw_frame_policy": [cfgp, vp, i64, vp, vp],
         "cw_render_alt": [cfgp, vp, vp, vp, i64, vp],
         "cw_host_create": [cfgp, i64, ci, u64, u64, ci, C.POINTER(vp)],
         "cw_host_reset": [vp, vp, vp],

@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
                 WarpPhilox rng;
                 uint32_t ag, gl;
                 reset_warp(cfg, st, env, nullptr, rng, ag, gl, env_ep);
-                if (lane_id() == src) { agent = ag; goal = gl; t = 0; ep = env_ep + 1; }
+                if (lane_id() == src) { agent = ag; goal = gl; t = 0; ep = env_ep + 1; if (st.init_agent) st.init_agent[env] = ag; }
             }
         }
     }
@@ -803,6 +803,35 @@ __global__ void __launch_bounds__(kExpThreads) cw_render_alt_kernel(const CwConf
         stream_out_same_phase<2>(buf, dst, nbytes, tid);
     }
     if (tid == 0) bulk_wait_all();
+}
+
+// A stand-in DEVICE CONSUMER of the frames (closed-loop measurements and tests): reads every byte of every world's frame and
+// turns it into that world's next action, so step k+1 depends on frame k the way it does under a policy network.
+//   h = sum_i word_i * (2 i + 1)  (uint32 words of the frame, wrap-around),  action = ((h ^ h >> 16) & 0xFFFF) % 6
+// One CTA per world (grid-stride), 16-byte streaming loads, warp-shuffle + shared-memory reduction.  Bound: HBM read.
+__global__ void __launch_bounds__(128) cw_frame_policy_kernel(const uint4* __restrict__ obs, int64_t n, uint32_t words16,
+                                                              uint8_t* __restrict__ actions) {
+    __shared__ uint32_t s_part[4];
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int64_t w = blockIdx.x; w < n; w += gridDim.x) {
+        const uint4* f = obs + (size_t)w * words16;
+        uint32_t h = 0;
+        for (uint32_t i = threadIdx.x; i < words16; i += 128) {
+            const uint4 v = __ldcs(f + i);
+            const uint32_t k = 8u * i + 1u;                       // 2 * (4 i) + 1
+            h += v.x * k + v.y * (k + 2u) + v.z * (k + 4u) + v.w * (k + 6u);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = h;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t t = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+            actions[w] = (uint8_t)(((t ^ (t >> 16)) & 0xFFFFu) % 6u);
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1156,6 +1185,20 @@ int cw_imagine(const CwConfig* cfg, const CwState* st, uint8_t* goal_obs, void* 
     EnvArgs a = {};
     a.goal_obs = goal_obs; a.mode = M_IMAGINE_ONLY;
     return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
+}
+
+int cw_frame_policy(const CwConfig* cfg, const uint8_t* obs, int64_t n, uint8_t* actions, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    if (n < 0) return CW_E_BADCONFIG;
+    if (n == 0) return 0;
+    if (!obs || !actions) return CW_E_NULLPTR;
+    if ((uintptr_t)obs & 15u) return CW_E_BADCONFIG;
+    DeviceInfo* dev;
+    rc = device_info(&dev); if (rc) return rc;
+    const int64_t blocks = n < (int64_t)dev->sms * 16 ? n : (int64_t)dev->sms * 16;
+    cudaError_t le = launch_pdl(cw_frame_policy_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream,
+                                reinterpret_cast<const uint4*>(obs), n, (uint32_t)(3 * cfg->H * cfg->W), actions);
+    return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 int cw_onehot(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, uint8_t* onehot, int64_t n, void* stream) {

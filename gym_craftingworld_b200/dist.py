@@ -19,16 +19,37 @@ def shard_range(total: int, rank: int, world: int):
 
 
 class StatsReducer:
-    """Periodic all-reduce of ``env.stats`` (backend-agnostic: NCCL on GPUs, gloo in the CPU tests)."""
+    """Periodic all-reduce of the episode statistics (backend-agnostic: NCCL on GPUs, gloo in the CPU tests).
 
-    def __init__(self, stats: torch.Tensor, every: int = 128, group=None, inline: bool = False):
+    ``stats`` must be the LIVE accumulator the kernels add to -- an env (its ``stats_raw`` is taken) or that tensor itself;
+    ``env.stats`` is a fresh sum on every access and would freeze the reducer on one snapshot, so it is refused.
+
+    Every reduction works on a SNAPSHOT: the accumulator is copied on the caller's (step) stream, i.e. between two step
+    launches, so all counters of the snapshot belong to the same step; the all-reduce of the copy then runs on a side
+    stream while later launches keep adding to the live accumulator.  Snapshots and results are double-buffered, and
+    :meth:`wait` orders the reader's stream after the reduction it returns.
+    """
+
+    def __init__(self, stats, every: int = 128, group=None, inline: bool = False):
         """``inline=True`` issues the all-reduce on the caller's stream instead of a side stream (it then costs its
         ~20-30 us latency once per ``every`` steps but never competes with the env kernel for SM slots)."""
+        if hasattr(stats, "stats_raw"):
+            stats = stats.stats_raw
+        if not isinstance(stats, torch.Tensor) or stats.dtype != torch.int64:
+            raise TypeError("StatsReducer needs the env or its live int64 `stats_raw` tensor")
+        if stats.dim() == 1 and stats.is_cuda:
+            raise ValueError("pass the env (or env.stats_raw, int64[16, 24]): env.stats is a detached copy and would never change")
         self.stats, self.every, self.group, self.inline = stats, int(every), group, bool(inline)
-        self.global_stats = torch.zeros_like(stats)
-        self._steps = 0
+        self._buf = [torch.zeros_like(stats), torch.zeros_like(stats)]
+        self._cur = 0                       # buffer of the most recent reduction
+        self._steps = self.reductions = 0
         self._side = torch.cuda.Stream(device=stats.device) if stats.is_cuda else None
+        self._done = [None, None]           # CUDA events: reduction into buffer i has finished
         self._work = None
+
+    @property
+    def global_stats(self) -> torch.Tensor:
+        return self._buf[self._cur]
 
     def step(self):
         """Call once per env step; launches the reduction every ``every`` steps."""
@@ -37,33 +58,44 @@ class StatsReducer:
             self.reduce_async()
 
     def reduce_async(self):
-        if not (dist.is_available() and dist.is_initialized()):
-            self.global_stats.copy_(self.stats)
-            return
+        nxt = self._cur ^ 1
+        out = self._buf[nxt]
+        self.reductions += 1
+        ready = dist.is_available() and dist.is_initialized()
         if self._side is None:                                    # CPU tensors (gloo): asynchronous work handle
-            self.global_stats.copy_(self.stats)
-            self._work = dist.all_reduce(self.global_stats, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if self._work is not None:
+                self._work.wait()
+            out.copy_(self.stats)
+            self._work = dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group, async_op=True) if ready else None
+            self._cur = nxt
             return
-        if self.inline:                                           # on the caller's stream, ordered with the env launches
-            self.global_stats.copy_(self.stats, non_blocking=True)
-            dist.all_reduce(self.global_stats, op=dist.ReduceOp.SUM, group=self.group)
-            return
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(self.stats.device))
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(ready)
-            self.global_stats.copy_(self.stats, non_blocking=True)
-            dist.all_reduce(self.global_stats, op=dist.ReduceOp.SUM, group=self.group)
+        main = torch.cuda.current_stream(self.stats.device)
+        if self._done[nxt] is not None:
+            main.wait_event(self._done[nxt])                      # the reduction that last used this buffer (two back) is over
+        out.copy_(self.stats, non_blocking=True)                  # the snapshot: on the step stream, between two launches
+        if self.inline or not ready:
+            if ready:
+                dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+            self._done[nxt] = main.record_event()
+        else:
+            snap = main.record_event()
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(snap)
+                dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+                self._done[nxt] = self._side.record_event()
+        self._cur = nxt
 
     def total(self) -> torch.Tensor:
-        """Global statistics vector; sums the device replicas when the reducer was given ``env.stats_raw``."""
+        """Global statistics vector ``int64[24]`` of the last reduction (the device replicas summed)."""
         g = self.wait()
         return g.sum(dim=0) if g.dim() == 2 else g
 
     def wait(self) -> torch.Tensor:
+        """The result of the most recent reduction; the caller's stream is ordered after it."""
         if self._work is not None:
             self._work.wait()
             self._work = None
-        if self._side is not None and not self.inline:
-            torch.cuda.current_stream(self.stats.device).wait_stream(self._side)
-        return self.global_stats
+        ev = self._done[self._cur]
+        if ev is not None:
+            torch.cuda.current_stream(self.stats.device).wait_event(ev)
+        return self._buf[self._cur]

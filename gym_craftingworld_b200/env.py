@@ -203,11 +203,12 @@ class BatchedCraftingWorldEnv:
             if self.goal_images:
                 self.desired_goal = torch.zeros(self.frame_shape, dtype=torch.uint8, device=dev)
                 self.init_obs = torch.zeros(self.frame_shape, dtype=torch.uint8, device=dev)
-        self.goal_grid = self.goal_agent = self.init_agent = None
-        if obs_mode == "onehot":                  # compact imagined goal state + INIT agent word (one-hot family)
+        self.goal_grid = self.goal_agent = None
+        # agent word at reset = the agent / holding channels of INIT_OBS_VECTOR (ray.py:183); 4 bytes per world, kept in every mode
+        self.init_agent = torch.zeros(N, dtype=torch.int32, device=dev)
+        if obs_mode == "onehot":                  # compact imagined goal state (one-hot family)
             self.goal_grid = torch.zeros((N, stride), dtype=torch.uint8, device=dev)
             self.goal_agent = torch.zeros(N, dtype=torch.int32, device=dev)
-            self.init_agent = torch.zeros(N, dtype=torch.int32, device=dev)
         self._obs_version = 0
         self._chain = None                        # chain words of cw_step_render_chained (allocated on first use)
         self._edit_scratch = None                 # work list of cw_step_render_edit (allocated on first use)
@@ -318,10 +319,10 @@ class BatchedCraftingWorldEnv:
 
     @property
     def observation_vector(self):
-        """``ray.py:185-187``; note ``init_observation`` carries the CURRENT agent/holding channels (the kernels keep
-        only the object codes of INIT_OBS_VECTOR, which is all the hot path ever reads)."""
+        """``ray.py:185-187``: one-hot state, 9-bit goal vectors and ``INIT_OBS_VECTOR`` (object codes of ``init_grid`` plus
+        the agent / holding channels as they were at reset, ``init_agent``)."""
         return {"observation": self.onehot(), "desired_goal": self.desired_goal_vector,
-                "achieved_goal": self.achieved_goal_vector, "init_observation": self.onehot(init=True)}
+                "achieved_goal": self.achieved_goal_vector, "init_observation": self.onehot(grid=self.init_grid, agent=self.init_agent)}
 
     # ---- observations ----------------------------------------------------------------------------------
     def _observation(self):
@@ -366,8 +367,14 @@ class BatchedCraftingWorldEnv:
             a = a.to(self.device)
         if self.validate_actions and bool(((a < 0) | (a >= len(self.ACTIONS))).any()):
             raise IndexError("action out of range [0, 6)")                                  # ray.py:308
+        return self._to_u8_actions(a)
+
+    @staticmethod
+    def _to_u8_actions(a):
+        """uint8 action codes; an out-of-range value of a wider dtype (260, -252, ...) must stay out of range -- the documented
+        no-op -- instead of wrapping modulo 256 onto a real action."""
         if a.dtype != torch.uint8:
-            a = a.to(torch.uint8)
+            a = torch.where((a < 0) | (a > 5), 6, a).to(torch.uint8)
         return a.contiguous()
 
     def step(self, actions, chain_pos=None):
@@ -426,11 +433,23 @@ class BatchedCraftingWorldEnv:
         self._obs_version += 1
         return self._observation(), self.reward, self.done, self._info
 
+    def frame_policy(self, obs=None, out=None):
+        """A stand-in device consumer (``cw_frame_policy``): reads every byte of every frame of ``obs`` (default: the current
+        observation) and returns ``uint8[N]`` actions derived from the pixels -- closes the loop the way a policy network
+        does, for measurements and tests.  Asynchronous on the current stream, CUDA-graph capturable."""
+        obs = self.obs if obs is None else obs
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cw_frame_policy(C.byref(self.cfg), obs.data_ptr(), self.num_envs, out.data_ptr(), self._stream()),
+                       "cw_frame_policy")
+        return out
+
     def rollout(self, actions, return_trace=True):
         """K steps in ONE launch on an open-loop action tape ``uint8[K, N]`` (compact observations only).
         Returns ``(reward int32[K,N], done bool[K,N])`` or ``None`` when ``return_trace`` is False."""
         a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions), device=self.device)
-        a = a.to(device=self.device, dtype=torch.uint8).contiguous()
+        a = self._to_u8_actions(a.to(device=self.device))
         if a.dim() != 2 or a.shape[1] != self.num_envs:
             raise ValueError(f"actions must have shape (K, {self.num_envs})")
         K = a.shape[0]
@@ -511,6 +530,7 @@ class BatchedCraftingWorldEnv:
             self.t.zero_()
         else:
             self.t.copy_(vec(t))
+        self.init_agent.copy_(self.agent)
         if self.obs_mode == "pixels":
             self.render()
             if self.goal_images:
@@ -519,7 +539,6 @@ class BatchedCraftingWorldEnv:
                     _lib.check(self._lib.cw_imagine(C.byref(self.cfg), C.byref(self._state), self.desired_goal.data_ptr(),
                                                     self._stream()), "cw_imagine")
         elif self.obs_mode == "onehot":
-            self.init_agent.copy_(self.agent)
             with torch.cuda.device(self.device):
                 _lib.check(self._lib.cw_imagine(C.byref(self.cfg), C.byref(self._state), None, self._stream()), "cw_imagine")
         self._is_reset = True
@@ -626,9 +645,10 @@ class BatchedCraftingWorldEnvAltObs(BatchedCraftingWorldEnv):
                                   spaces.Dict(dict(observation=img, desired_goal=img, achieved_goal=img, init_observation=img)))
 
     def render_alt(self, grid, agent):
-        out = torch.empty((self.num_envs, 3 * self.cfg.H + 3, 3 * self.cfg.W, 3), dtype=torch.int16, device=self.device)
+        M = grid.shape[0]
+        out = torch.empty((M, 3 * self.cfg.H + 3, 3 * self.cfg.W, 3), dtype=torch.int16, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.cw_render_alt(C.byref(self.cfg), grid.data_ptr(), agent.data_ptr(), out.data_ptr(), self.num_envs,
+            _lib.check(self._lib.cw_render_alt(C.byref(self.cfg), grid.data_ptr(), agent.data_ptr(), out.data_ptr(), M,
                                                self._stream()), "cw_render_alt")
         return out
 
@@ -639,6 +659,14 @@ class BatchedCraftingWorldEnvAltObs(BatchedCraftingWorldEnv):
         return obs
 
     def render(self, state=None, mode="Non", tile_size=4):
-        if state is not None:
-            raise NotImplementedError("AltObs render of foreign states: use render_alt(grid, agent)")
-        return self.render_alt(self.grid, self.agent)
+        """``render`` (``craftingworld_altobs.py:489-548``): the current worlds, or foreign states given as
+        ``(grid uint8[M,H,W], r[M], c[M], hold[M])`` -> a fresh ``int16[M, 3H+3, 3W, 3]`` tensor."""
+        if state is None:
+            return self.render_alt(self.grid, self.agent)
+        H, W = self.cfg.H, self.cfg.W
+        g, r, c, h = state
+        g = torch.as_tensor(g, device=self.device).to(torch.uint8).reshape(-1, H * W)
+        grid = torch.zeros((g.shape[0], self.cfg.cell_stride), dtype=torch.uint8, device=self.device)
+        grid[:, :H * W] = g
+        r, c, h = (torch.as_tensor(x, device=self.device).to(torch.int32).reshape(-1) for x in (r, c, h))
+        return self.render_alt(grid, (r | (c << 8) | (h << 16)).contiguous())

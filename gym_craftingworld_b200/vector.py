@@ -61,18 +61,38 @@ class CraftingWorldVectorEnv:
         self.closed = True
 
 
-def register_envs(num_envs=4096):
-    """Register ``craftingworld-b200-v3`` with gymnasium or gym when importable (mirrors
-    ``gym_craftingworld/__init__.py:5-18``).  Returns the ids registered (empty when neither package exists)."""
-    for mod in ("gymnasium", "gym"):
-        try:
-            reg = __import__(mod + ".envs.registration", fromlist=["register"]).register
-        except Exception:  # noqa: BLE001
-            continue
-        reg(id="craftingworld-b200-v3", entry_point="gym_craftingworld_b200:BatchedCraftingWorldEnv",
-            kwargs={"num_envs": num_envs, "stacking": True})
-        return ["craftingworld-b200-v3"]
-    return []
+# the reference's three registrations (gym_craftingworld/__init__.py:5-18): id -> (its entry-point class, our batched mirror)
+REGISTRATIONS = {
+    "craftingworld-v3": ("CraftingWorldEnvRay", "BatchedCraftingWorldEnv"),
+    "craftingworldflat-v3": ("CraftingWorldEnvFlat", "BatchedCraftingWorldEnvFlat"),
+    "craftingworldonehot-v3": ("CraftingWorldEnvOneHot", "BatchedCraftingWorldEnvOneHot"),
+}
+
+
+def register_envs(num_envs=4096, reference_ids=False, register=None):
+    """Register the three batched mirrors with gymnasium or gym when one of them is importable -- what
+    ``gym_craftingworld/__init__.py:5-18`` does for the reference: the same three environments with the same ``kwargs``
+    (``stacking=True, render_save_rate=10``) plus ``num_envs``.  By default the ids carry a ``-b200`` tag
+    (``craftingworld-b200-v3``, ``craftingworldflat-b200-v3``, ``craftingworldonehot-b200-v3``) so that both packages can
+    be installed side by side; ``reference_ids=True`` registers the reference's own ids instead (a drop-in for code that
+    calls ``gym.make('craftingworld-v3')``).  ``register`` overrides the registration function (tests).
+    Returns the ids registered (empty when neither package exists)."""
+    if register is None:
+        for mod in ("gymnasium", "gym"):
+            try:
+                register = __import__(mod + ".envs.registration", fromlist=["register"]).register
+                break
+            except Exception:  # noqa: BLE001
+                continue
+    if register is None:
+        return []
+    ids = []
+    for ref_id, (_, cls) in REGISTRATIONS.items():
+        env_id = ref_id if reference_ids else ref_id.replace("-v3", "-b200-v3")
+        register(id=env_id, entry_point=f"gym_craftingworld_b200:{cls}",
+                 kwargs={"num_envs": num_envs, "stacking": True, "render_save_rate": 10})
+        ids.append(env_id)
+    return ids
 
 
 class GifRecorder:

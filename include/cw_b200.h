@@ -185,6 +185,12 @@ int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, i
  * (seed, global id, episode[n]).  For states injected with load_state. */
 int cw_imagine(const CwConfig* cfg, const CwState* st, uint8_t* goal_obs, void* stream);
 
+/* A stand-in device-side CONSUMER of the frames, for closed-loop measurements and tests (the reference has no counterpart: its
+ * consumer is the user's policy): reads every byte of each world's frame obs[n] (uint8[4H][4W][3], 16-byte aligned) and derives
+ * that world's next action from it,  h = sum_i word_i * (2 i + 1) over the frame's uint32 words (wrap-around),
+ * actions[n] = ((h ^ h >> 16) & 0xFFFF) % 6.  Step k+1 then depends on frame k the way it does under a policy network. */
+int cw_frame_policy(const CwConfig* cfg, const uint8_t* obs, int64_t n, uint8_t* actions, void* stream);
+
 /* One-hot observation_vector (ray.py:94-98, 605-613; the obs of CraftingWorldEnvOneHot): uint8[N][H][W][12],
  * channels 0..7 objects, 8 agent, 9..11 holding sticks/axe/hammer (at the agent cell). */
 int cw_onehot(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agent, uint8_t* onehot, int64_t n,

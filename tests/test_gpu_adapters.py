@@ -194,19 +194,132 @@ def test_onehot_and_altobs_kernels_match_oracle_on_dense_states(cw, N, size):
 
 
 def test_vector_env_facade(cw):
-    venv = cw.CraftingWorldVectorEnv(32, size=(5, 5), max_steps=6, seed=3)
-    obs, info = venv.reset(seed=3)
-    assert obs["observation"].shape == (32, 20, 20, 3) and info == {}
-    seen_trunc = False
-    for k in range(12):
-        obs, reward, terminated, truncated, info = venv.step(torch.randint(0, 6, (32,), device="cuda", dtype=torch.uint8))
+    """gymnasium.vector-shaped facade: call shapes, terminated / truncated split, and every value against the oracle."""
+    from oracle import native
+    N, size, max_steps, seed = 48, 5, 6, 3
+    venv = cw.CraftingWorldVectorEnv(N, size=(size, size), max_steps=max_steps, seed=seed)
+    ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed)
+    obs, info = venv.reset(seed=seed)
+    o_goal = ob.reset(with_goal=True)
+    o_obs = ob.render()
+    assert obs["observation"].shape == (N, 20, 20, 3) and info == {}
+    assert np.array_equal(obs["observation"].cpu().numpy(), o_obs) and np.array_equal(obs["desired_goal"].cpu().numpy(), o_goal)
+    rng = np.random.RandomState(1)
+    seen_trunc = seen_term = False
+    for k in range(40):
+        a = rng.randint(0, 6, N).astype(np.uint8)
+        venv.step_async(torch.from_numpy(a).cuda())
+        obs, reward, terminated, truncated, info = venv.step_wait()
+        o_reward, o_done = ob.step_full(a, auto_reset=True, obs=o_obs)
+        assert np.array_equal(reward.cpu().numpy(), o_reward)
+        assert np.array_equal(terminated.cpu().numpy(), o_reward == max_steps)
+        assert np.array_equal((terminated | truncated).cpu().numpy(), o_done.astype(bool))
         assert not bool((terminated & truncated).any())
-        assert bool(((reward == 6) == terminated).all())
-        seen_trunc |= bool(truncated.any())
+        assert np.array_equal(obs["observation"].cpu().numpy(), o_obs), k
+        assert np.array_equal(info["achieved_mask"].cpu().numpy().astype(np.uint32), ob.goal & 0xFFFF)
+        assert np.array_equal(info["desired_mask"].cpu().numpy().astype(np.uint32), ob.goal >> 16)
+        seen_trunc |= bool(truncated.any()); seen_term |= bool(terminated.any())
     assert seen_trunc and set(info) == {"achieved_mask", "desired_mask"}
     nv = cw.CraftingWorldVectorEnv(8, to_numpy=True, size=(5, 5), seed=0)
     o, _ = nv.reset()
     assert isinstance(o["observation"], np.ndarray)
+
+
+def test_registered_entry_points_construct_the_mirrors(cw):
+    """What gym.make would do with the three registrations: import the entry point, call it with the registered kwargs."""
+    import importlib
+    made = {}
+    cw.register_envs(num_envs=16, register=lambda id, entry_point, kwargs: made.__setitem__(id, (entry_point, kwargs)))
+    kinds = {}
+    for env_id, (entry, kwargs) in made.items():
+        mod, cls = entry.split(":")
+        env = getattr(importlib.import_module(mod), cls)(**kwargs)
+        obs = env.reset()
+        kinds[env_id] = type(env).__name__
+        assert env.num_envs == 16 and env.stacking is True
+        first = obs if isinstance(obs, torch.Tensor) else obs["observation"]
+        assert first.shape[0] == 16
+    assert kinds == {"craftingworld-b200-v3": "BatchedCraftingWorldEnv", "craftingworldflat-b200-v3": "BatchedCraftingWorldEnvFlat",
+                     "craftingworldonehot-b200-v3": "BatchedCraftingWorldEnvOneHot"}
+
+
+def test_init_observation_vector_keeps_the_initial_agent_channels(cw):
+    """`observation_vector['init_observation']` is INIT_OBS_VECTOR (ray.py:183-187): object AND agent / holding channels as they
+    were at reset -- in pixel mode too, through auto-resets, and for the compact step kernel."""
+    from oracle import native
+    N, size, max_steps, seed = 300, 6, 5, 12
+    for mode in ("pixels", "compact"):
+        env = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=seed, obs_mode=mode)
+        ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed)
+        env.reset(); ob.reset()
+        init_agent = ob.agent.copy()
+        rng = np.random.RandomState(0)
+        for k in range(17):
+            a = rng.randint(0, 6, N).astype(np.uint8)
+            env.step(torch.from_numpy(a).cuda())
+            _, o_done = ob.step_full(a, auto_reset=True)
+            init_agent[o_done == 1] = ob.agent[o_done == 1]         # a re-seeded world starts a new INIT_OBS_VECTOR
+        assert np.array_equal(env.init_agent.cpu().numpy().astype(np.uint32), init_agent), mode
+        vec = env.observation_vector["init_observation"].cpu().numpy()
+        want = np.zeros((N, size, size, 12), np.uint8)
+        ig = ob.init_grid[:, :size * size].reshape(N, size, size)
+        for ch in range(8):
+            want[..., ch] = ig == ch + 1
+        want[np.arange(N), init_agent & 0xFF, (init_agent >> 8) & 0xFF, 8] = 1
+        assert np.array_equal(vec, want), mode
+        assert (env.agent.cpu().numpy().astype(np.uint32) != init_agent).any()          # (the current agent words differ)
+
+
+def test_altobs_render_of_foreign_states(cw):
+    """AltObs `render(state)` (craftingworld_altobs.py:489): frames of states that are NOT the env's own (a different count
+    of them, too), against the frames frozen from the reference's AltObs renderer."""
+    src, frame_t, frames = gu.load_altobs()
+    d = gu.load(src)
+    env = cw.BatchedCraftingWorldEnvAltObs(3, size=(8, 8), seed=0)
+    env.reset()
+    before = env.render().clone()
+    for i, t in enumerate(frame_t[:4]):
+        got = env.render((d["grid"][:, t], d["r"][:, t], d["c"][:, t], d["hold"][:, t])).cpu().numpy()
+        assert got.shape == frames[:, i].shape and np.array_equal(got, frames[:, i]), t
+    assert torch.equal(env.render(), before)                       # the env's own worlds are untouched
+
+
+def test_out_of_range_actions_of_wide_dtypes_stay_no_ops(cw):
+    """260 or -252 must not wrap modulo 256 onto 'pickup': an out-of-range action is a no-op that still advances step_num."""
+    N = 64
+    a = cw.BatchedCraftingWorldEnv(N, size=(5, 5), max_steps=50, seed=4, auto_reset=False)
+    b = cw.BatchedCraftingWorldEnv(N, size=(5, 5), max_steps=50, seed=4, auto_reset=False)
+    a.reset(); b.reset()
+    for k in range(10):                                             # put some agents onto pickupable objects
+        acts = torch.randint(0, 4, (N,), device="cuda")
+        a.step(acts); b.step(acts)
+    wide = torch.tensor([260, -252, 6, 1000] * (N // 4), device="cuda", dtype=torch.int64)
+    a.step(wide)
+    b.step(torch.full((N,), 6, device="cuda", dtype=torch.uint8))
+    for key in ("grid", "agent", "goal", "t", "reward"):
+        assert torch.equal(getattr(a, key), getattr(b, key)), key
+    assert bool((a.t == 11).all())
+
+
+def test_frame_policy_consumer_reads_every_byte(cw):
+    """cw_frame_policy (the stand-in device consumer of the closed-loop bench leg): its actions equal the NumPy restatement of
+    the hash, and flipping ONE byte of a frame changes the hash."""
+    for size, N in ((21, 300), (5, 33), (32, 17)):
+        env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=size)
+        obs = env.reset()["observation"]
+        got = env.frame_policy().cpu().numpy()
+        words = obs.cpu().numpy().reshape(N, -1).view(np.uint32).astype(np.uint64)
+        k = (2 * np.arange(words.shape[1], dtype=np.uint64) + 1)
+        h = ((words * k) & 0xFFFFFFFF).sum(axis=1) & 0xFFFFFFFF
+        want = ((h ^ (h >> 16)) & 0xFFFF) % 6
+        assert np.array_equal(got, want.astype(np.uint8)), size
+    obs2 = obs.clone()
+    obs2[3, -1, -1, 2] ^= 1                                        # the very last byte of world 3
+    w2 = obs2.cpu().numpy().reshape(N, -1).view(np.uint32).astype(np.uint64)
+    assert (((w2 * k) & 0xFFFFFFFF).sum(axis=1) & 0xFFFFFFFF)[3] != h[3]
+    got2 = env.frame_policy(obs2).cpu().numpy()
+    want2 = ((( ((w2 * k) & 0xFFFFFFFF).sum(axis=1) & 0xFFFFFFFF) ^ ((((w2 * k) & 0xFFFFFFFF).sum(axis=1) & 0xFFFFFFFF) >> 16)) & 0xFFFF) % 6
+    assert np.array_equal(got2, want2.astype(np.uint8))
 
 
 def test_integration_md_ctypes_stub_runs(cw):

@@ -110,6 +110,34 @@ def test_gif_recorder_writes_episode_gifs(tmp_path):
     assert cw.register_envs() == []                       # neither gym nor gymnasium is installed here
 
 
+def test_registration_mirrors_the_references_three_ids():
+    """`gym_craftingworld/__init__.py:5-18` registers craftingworld-v3 / craftingworldflat-v3 / craftingworldonehot-v3 with
+    kwargs stacking=True, render_save_rate=10: the batched mirrors register the same three (tagged -b200, or under the
+    reference's own ids), same kwargs + num_envs, and every entry point resolves to a class that accepts them."""
+    import importlib
+    import inspect
+    seen = {}
+    ids = cw.register_envs(num_envs=64, register=lambda id, entry_point, kwargs: seen.__setitem__(id, (entry_point, kwargs)))
+    assert ids == ["craftingworld-b200-v3", "craftingworldflat-b200-v3", "craftingworldonehot-b200-v3"]
+    seen_ref = {}
+    assert cw.register_envs(reference_ids=True, register=lambda id, entry_point, kwargs: seen_ref.__setitem__(id, (entry_point, kwargs))) == \
+        ["craftingworld-v3", "craftingworldflat-v3", "craftingworldonehot-v3"]
+    for env_id, (entry, kwargs) in seen.items():
+        assert kwargs == {"num_envs": 64, "stacking": True, "render_save_rate": 10}
+        mod, cls = entry.split(":")
+        klass = getattr(importlib.import_module(mod), cls)
+        params = inspect.signature(klass.__init__).parameters
+        assert "num_envs" in params and (("stacking" in params and "render_save_rate" in params) or "kw" in params or "args" in params)
+    from oracle import ref_shim
+    if ref_shim.reference_available():                    # the reference's own registry: same ids, same kwargs (minus num_envs)
+        ref_shim.load_reference()
+        import sys
+        reg = sys.modules["gym.envs.registration"].registry
+        for ref_id, (ref_cls, _) in cw.vector.REGISTRATIONS.items():
+            entry, kwargs = reg[ref_id]
+            assert entry.endswith(":" + ref_cls) and kwargs == {k: v for k, v in seen_ref[ref_id][1].items() if k != "num_envs"}
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (CPU only): exactly one JSON line on stdout with the contract's keys."""
     import json
@@ -125,7 +153,9 @@ def test_bench_reference_arm_contract():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
-    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    import os
+    installed = os.path.isfile(os.path.join(root, "oracle", "_ref", "gym_craftingworld", "envs", "craftingworld_ray.py"))
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == ("reference" if installed else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
