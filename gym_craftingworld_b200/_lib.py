@@ -18,7 +18,7 @@ F_AUTO_RESET = 1
 F_DELTA_TRANSPORT = 2
 
 # every symbol include/cw_b200.h declares (tests check the library exports exactly these)
-SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_step_render_chained", "cw_step_render_edit", "cw_step_delta", "cw_rollout",
+SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_step_render_chained", "cw_step_render_edit", "cw_step_delta", "cw_rollout", "cw_prefill_resets",
            "cw_imagine", "cw_frame_policy", "cw_onehot", "cw_render_alt", "cw_host_create", "cw_host_reset", "cw_host_bind_actions", "cw_host_step",
            "cw_host_step_many", "cw_host_load_state", "cw_host_stats", "cw_host_device_state", "cw_host_stream", "cw_host_fetch_frames", "cw_host_sync",
            "cw_host_destroy"]
@@ -34,7 +34,8 @@ class CwState(C.Structure):
     _fields_ = [("grid", C.c_void_p), ("init_grid", C.c_void_p), ("agent", C.c_void_p), ("goal", C.c_void_p),
                 ("t", C.c_void_p), ("episode", C.c_void_p), ("n", C.c_int64), ("seed", C.c_uint64),
                 ("env_id_base", C.c_uint64), ("fixed_grid", C.c_void_p), ("fixed_agent", C.c_void_p),
-                ("n_fixed", C.c_int64), ("goal_grid", C.c_void_p), ("goal_agent", C.c_void_p), ("init_agent", C.c_void_p)]
+                ("n_fixed", C.c_int64), ("goal_grid", C.c_void_p), ("goal_agent", C.c_void_p), ("init_agent", C.c_void_p),
+                ("reset_rec", C.c_void_p), ("reset_list", C.c_void_p)]
 
 
 class CwError(RuntimeError):
@@ -61,6 +62,7 @@ def _declare(lib):
         "cw_rollout": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
         "cw_step_delta": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
         "cw_imagine": [cfgp, stp, vp, vp],
+        "cw_prefill_resets": [cfgp, stp, vp],
         "cw_onehot": [cfgp, vp, vp, vp, i64, vp],
         "cw_frame_policy": [cfgp, vp, i64, vp, vp],
         "cw_render_alt": [cfgp, vp, vp, vp, i64, vp],

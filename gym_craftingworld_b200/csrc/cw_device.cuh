@@ -193,21 +193,35 @@ __device__ __forceinline__ void stats_add(const CwConfig& cfg, unsigned long lon
     }
 }
 
-// ------------------------------------------------------------------------------------------------------
-// reset(): ray.py:156-218, executed by one full warp for world `n`.
-// Draw order (spec: oracle/compact.py reset_env): task count, task subset (169-174), placement (605-613).
-// Writes grid + init_grid (global; and `sg` if non-null, a shared copy) and episode[n]; returns agent/goal.
-// `rng` is left positioned after the placement draws so imagine_warp can continue the same stream.
-// ------------------------------------------------------------------------------------------------------
 struct Sparse8 {   // a world with (at most) one object per entry: cell index + object code, static indexing only
     uint32_t cell[8];
     uint32_t code[8];
 };
 
-__device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& st, int64_t n, uint8_t* sg, WarpPhilox& rng,
-                                           uint32_t& agent_out, uint32_t& goal_out, uint32_t ep, Sparse8* objs = nullptr,
-                                           uint32_t* s_scratch = nullptr) {
-    // `ep` = st.episode[n], loaded by the caller together with the world's other scalars (no dependent load here)
+// desired_goal_vector: n_tasks = U{1..number_of_tasks} if stacking else 1; partial Fisher-Yates over selected_tasks, kept as
+// 4-bit entries of one 64-bit word (ray.py:169-174).  Serial walk of the stream (the spec, oracle/compact.py).
+__device__ __forceinline__ uint32_t reset_tasks_serial(const CwConfig& cfg, WarpPhilox& rng) {
+    uint64_t perm = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) perm |= (uint64_t)(cfg.selected[i] & 15) << (4 * i);
+    uint32_t des = 0;
+    const int ntask = cfg.stacking ? (int)rng.uniform((uint32_t)cfg.number_of_tasks) + 1 : 1;
+    for (int i = 0; i < ntask; i++) {
+        const int j = i + (int)rng.uniform((uint32_t)(cfg.n_selected - i));
+        const uint64_t vi = (perm >> (4 * i)) & 15, vj = (perm >> (4 * j)) & 15;
+        perm = (perm & ~((uint64_t)15 << (4 * i)) & ~((uint64_t)15 << (4 * j))) | (vj << (4 * i)) | (vi << (4 * j));
+        des |= 1u << (uint32_t)vj;
+    }
+    return des;
+}
+
+// The RANDOM part of reset() for a world without a fixed pool: task sampling (ray.py:169-174) + sample_state's 9 distinct
+// cells (605-613; cells[0..7] the objects sticks..wheat, cells[8] the agent), by one full warp, from the stream
+// (seed, global id of world n, episode ep).  Writes nothing: the result depends only on (seed, id, ep), so it can be drawn
+// long before the reset happens (cw_step_kernel's pre-drawn reset records).  `rng` is left positioned after the placement
+// draws so imagine_* can continue the same stream.
+__device__ __forceinline__ void reset_sample(const CwConfig& cfg, const CwState& st, int64_t n, WarpPhilox& rng, uint32_t ep,
+                                             uint32_t& des_out, uint32_t (&cells)[9]) {
     const int lane = lane_id();
     rng.init(st.seed, st.env_id_base + (uint64_t)n, ep);
     rng.refill();                                                // 128 draws buffered: draw j = lane j>>2, slot j&3
@@ -216,7 +230,6 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
 #pragma unroll
     for (int i = 0; i < 9; i++) perm |= (uint64_t)(cfg.selected[i] & 15) << (4 * i);
     uint32_t des = 0;
-    uint32_t cells[9];
     bool sampled = false;
     // ---- lane-parallel sampling with exact redraw semantics --------------------------------------------------------
     // The serial algorithm (the fallback below; spec: oracle/compact.py) walks the stream: draw i+1 follows the last draw
@@ -224,7 +237,7 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
     // Here lane i evaluates position i from stream offset (base + i + shift_i); the FIRST violating position k is exactly
     // where the serial loop would redraw, so all positions >= k move one draw forward and the round repeats.  Rounds are
     // rare (8 % of resets at 21x21 need one), every round is a handful of shuffles instead of a dependent loop.
-    if (st.n_fixed == 0) {
+    {
         auto fetch = [&](int d) {                                // draw d (per lane) of the buffered 128-draw block
             const int src = d >> 2, sl = d & 3;
             const uint32_t a0 = __shfl_sync(0xffffffffu, rng.w0, src), a1 = __shfl_sync(0xffffffffu, rng.w1, src);
@@ -289,88 +302,108 @@ __device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& s
         }
     }
     if (!sampled) {
-        // desired_goal_vector: n_tasks = U{1..number_of_tasks} if stacking else 1; partial Fisher-Yates over
-        // selected_tasks, kept as 4-bit entries of one 64-bit word (ray.py:169-174)
-        const int ntask = cfg.stacking ? (int)rng.uniform((uint32_t)cfg.number_of_tasks) + 1 : 1;
-        for (int i = 0; i < ntask; i++) {
-            const int j = i + (int)rng.uniform((uint32_t)(cfg.n_selected - i));
-            const uint64_t vi = (perm >> (4 * i)) & 15, vj = (perm >> (4 * j)) & 15;
-            perm = (perm & ~((uint64_t)15 << (4 * i)) & ~((uint64_t)15 << (4 * j))) | (vj << (4 * i)) | (vi << (4 * j));
-            des |= 1u << (uint32_t)vj;
+        des = reset_tasks_serial(cfg, rng);
+#pragma unroll
+        for (int k = 0; k < 9; k++) {                            // sample_state: 9 distinct uniform cells (ray.py:605-613)
+            uint32_t cell;
+            bool dup;
+            do {
+                cell = rng.uniform(ncell);
+                dup = false;
+#pragma unroll
+                for (int q = 0; q < k; q++) dup |= cells[q] == cell;
+            } while (dup);
+            cells[k] = cell;
         }
     }
+    des_out = des;
+}
+
+// The DETERMINISTIC part of reset() (ray.py:176-203) for a drawn placement: grid + init_grid rows as 16-byte chunks composed in
+// registers (one chunk per lane per pass; `sg`, if non-null, receives a shared-memory copy), episode counter, agent / goal words.
+__device__ __forceinline__ void reset_apply(const CwConfig& cfg, const CwState& st, int64_t n, uint8_t* sg, uint32_t des,
+                                            const uint32_t (&cells)[9], uint32_t ep, uint32_t& agent_out, uint32_t& goal_out,
+                                            Sparse8* objs = nullptr) {
+    const int lane = lane_id();
     const int nchunk = cfg.cell_stride >> 4;
     uint4* gg = reinterpret_cast<uint4*>(st.grid + n * cfg.cell_stride);
     uint4* gi = reinterpret_cast<uint4*>(st.init_grid + n * cfg.cell_stride);
-    uint32_t agent_new;
-    if (st.n_fixed > 0) {
-        // generate_fixed_initial_state: uniform pick from the pre-sampled pool (ray.py:636-644)
-        const uint32_t idx = rng.uniform((uint32_t)st.n_fixed);
-        const uint4* src = reinterpret_cast<const uint4*>(st.fixed_grid + (size_t)idx * cfg.cell_stride);
-        for (int ch = lane; ch < nchunk; ch += 32) {
-            const uint4 v4 = src[ch];
-            gg[ch] = v4;
-            gi[ch] = v4;
-            if (sg) reinterpret_cast<uint4*>(sg)[ch] = v4;
-        }
-        agent_new = st.fixed_agent[idx] & 0xFFFFu;
-        if (objs) {   // object list of the pooled world (one of each code): found by one pass over the tile
-            __syncwarp();
-            for (int ch = lane; ch < nchunk; ch += 32) {
-                const uint4 v4 = src[ch];
-                const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+    for (int ch = lane; ch < nchunk; ch += 32) {
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll
-                for (int b = 0; b < 16; b++) {
-                    const uint32_t c = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
-                    if (c >= 1 && c <= 8) s_scratch[c - 1] = (uint32_t)(16 * ch + b);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 8; k++) { objs->cell[k] = s_scratch[k]; objs->code[k] = (uint32_t)(k + 1); }
-            __syncwarp();
-        }
-    } else {
-        // sample_state: 8 objects + agent on 9 distinct uniform cells (ray.py:605-613)
-        if (!sampled) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-                uint32_t cell;
-                bool dup;
-                do {
-                    cell = rng.uniform(ncell);
-                    dup = false;
-#pragma unroll
-                    for (int q = 0; q < k; q++) dup |= cells[q] == cell;
-                } while (dup);
-                cells[k] = cell;
+        for (int k = 0; k < 8; k++) {
+            if ((int)(cells[k] >> 4) == ch) {
+                const uint32_t v = (uint32_t)(k + 1) << (8 * (cells[k] & 3));
+                const int wi = (cells[k] >> 2) & 3;
+                w0 |= wi == 0 ? v : 0; w1 |= wi == 1 ? v : 0; w2 |= wi == 2 ? v : 0; w3 |= wi == 3 ? v : 0;
             }
         }
-        // grid rows as 16-byte chunks, composed in registers (one chunk per lane per iteration)
-        for (int ch = lane; ch < nchunk; ch += 32) {
-            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        const uint4 v4 = make_uint4(w0, w1, w2, w3);
+        gg[ch] = v4;
+        gi[ch] = v4;                                                         // INIT_OBS_VECTOR, ray.py:183
+        if (sg) reinterpret_cast<uint4*>(sg)[ch] = v4;
+    }
+    const uint32_t ar = cells[8] / (uint32_t)cfg.W;
+    if (objs) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if ((int)(cells[k] >> 4) == ch) {
-                    const uint32_t v = (uint32_t)(k + 1) << (8 * (cells[k] & 3));
-                    const int wi = (cells[k] >> 2) & 3;
-                    w0 |= wi == 0 ? v : 0; w1 |= wi == 1 ? v : 0; w2 |= wi == 2 ? v : 0; w3 |= wi == 3 ? v : 0;
-                }
-            }
-            const uint4 v4 = make_uint4(w0, w1, w2, w3);
-            gg[ch] = v4;
-            gi[ch] = v4;                                                         // INIT_OBS_VECTOR, ray.py:183
-            if (sg) reinterpret_cast<uint4*>(sg)[ch] = v4;
-        }
-        const uint32_t ar = cells[8] / (uint32_t)cfg.W;
-        agent_new = ar | ((cells[8] - ar * (uint32_t)cfg.W) << 8);
-        if (objs) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) { objs->cell[k] = cells[k]; objs->code[k] = (uint32_t)(k + 1); }
-        }
+        for (int k = 0; k < 8; k++) { objs->cell[k] = cells[k]; objs->code[k] = (uint32_t)(k + 1); }
     }
     if (lane == 0) st.episode[n] = ep + 1;
-    agent_out = agent_new;                                                       // holding nothing
+    agent_out = ar | ((cells[8] - ar * (uint32_t)cfg.W) << 8);                   // holding nothing
+    goal_out = des << 16;                                                        // achieved = 0, ray.py:176
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// reset(): ray.py:156-218, executed by one full warp for world `n`.
+// Draw order (spec: oracle/compact.py reset_env): task count, task subset (169-174), placement (605-613).
+// Writes grid + init_grid (global; and `sg` if non-null, a shared copy) and episode[n]; returns agent/goal.
+// `rng` is left positioned after the placement draws so imagine_warp can continue the same stream.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reset_warp(const CwConfig& cfg, const CwState& st, int64_t n, uint8_t* sg, WarpPhilox& rng,
+                                           uint32_t& agent_out, uint32_t& goal_out, uint32_t ep, Sparse8* objs = nullptr,
+                                           uint32_t* s_scratch = nullptr) {
+    // `ep` = st.episode[n], loaded by the caller together with the world's other scalars (no dependent load here)
+    if (st.n_fixed == 0) {
+        uint32_t des, cells[9];
+        reset_sample(cfg, st, n, rng, ep, des, cells);
+        reset_apply(cfg, st, n, sg, des, cells, ep, agent_out, goal_out, objs);
+        return;
+    }
+    // generate_fixed_initial_state: uniform pick from the pre-sampled pool (ray.py:636-644)
+    const int lane = lane_id();
+    rng.init(st.seed, st.env_id_base + (uint64_t)n, ep);
+    rng.refill();
+    const uint32_t des = reset_tasks_serial(cfg, rng);
+    const int nchunk = cfg.cell_stride >> 4;
+    uint4* gg = reinterpret_cast<uint4*>(st.grid + n * cfg.cell_stride);
+    uint4* gi = reinterpret_cast<uint4*>(st.init_grid + n * cfg.cell_stride);
+    const uint32_t idx = rng.uniform((uint32_t)st.n_fixed);
+    const uint4* src = reinterpret_cast<const uint4*>(st.fixed_grid + (size_t)idx * cfg.cell_stride);
+    for (int ch = lane; ch < nchunk; ch += 32) {
+        const uint4 v4 = src[ch];
+        gg[ch] = v4;
+        gi[ch] = v4;
+        if (sg) reinterpret_cast<uint4*>(sg)[ch] = v4;
+    }
+    if (objs) {   // object list of the pooled world (one of each code): found by one pass over the tile
+        __syncwarp();
+        for (int ch = lane; ch < nchunk; ch += 32) {
+            const uint4 v4 = src[ch];
+            const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const uint32_t c = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+                if (c >= 1 && c <= 8) s_scratch[c - 1] = (uint32_t)(16 * ch + b);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) { objs->cell[k] = s_scratch[k]; objs->code[k] = (uint32_t)(k + 1); }
+        __syncwarp();
+    }
+    if (lane == 0) st.episode[n] = ep + 1;
+    agent_out = st.fixed_agent[idx] & 0xFFFFu;                                   // holding nothing
     goal_out = des << 16;                                                        // achieved = 0, ray.py:176
     __syncwarp();
 }

@@ -452,17 +452,58 @@ __device__ __forceinline__ void frame_edit(const CwConfig& cfg, uint8_t* frame, 
     span6(pn + 2 * rowb + 3, hold ? kColorLUT[hold] : 0x00FFFFFFu);   // ray.py:556-557
 }
 
+// ---- pre-drawn reset records of the compact step kernel ---------------------------------------------------------------------
+// What a reset draws depends only on (seed, global id, episode), so it can be drawn BEFORE the episode ends.  st.reset_rec keeps
+// one 32-byte record per world as two self-validating 16-byte halves, each written and read with ONE 16-byte access:
+//     { episode tag, desired mask | agent cell << 16, cells 0|1, cells 2|3 }   { episode tag, cells 4|5, cells 6|7, 0 }
+// A finished world's warp then only copies the placement into the grid (reset_apply); the ~2500 dependent instructions of the
+// Philox sampling run in extra "refill" CTAs of the NEXT launch, next to -- not in front of -- the stepping warps.  A world
+// whose record is missing or stale (a tag of either half differs: first use, a 1-step episode whose successor is still being
+// drawn, a reset done elsewhere) falls back to the inline draw; both routes produce the same bits.  st.reset_list is the queue
+// between the two: [0] tail (appends so far), [1] limit (tail at the end of the previous launch), [2] head, [3] exit ticket,
+// then a ring of 2N world ids.
+constexpr int kListHeader = 4;
+__device__ __forceinline__ void reset_record_write(uint32_t* rec, uint32_t tag, uint32_t des, const uint32_t (&cells)[9]) {
+    const int lane = lane_id();
+    uint4 v = lane == 0 ? make_uint4(tag, des | (cells[8] << 16), cells[0] | (cells[1] << 16), cells[2] | (cells[3] << 16))
+                        : make_uint4(tag, cells[4] | (cells[5] << 16), cells[6] | (cells[7] << 16), 0u);
+    if (lane < 2) __stcg(reinterpret_cast<uint4*>(rec) + lane, v);
+}
+// refill warps: draw the next reset of every queued world (or of all worlds: prefill)
+__device__ __forceinline__ void reset_refill(const CwConfig& cfg, const CwState& st, int64_t first_warp, int64_t n_warps, bool all) {
+    uint32_t* list = st.reset_list;
+    const uint32_t cap = 2u * (uint32_t)st.n;
+    const uint32_t head = all ? 0u : __ldcg(list + 2), limit = all ? (uint32_t)st.n : __ldcg(list + 1);
+    for (uint32_t i = head + (uint32_t)first_warp; (int32_t)(limit - i) > 0; i += (uint32_t)n_warps) {
+        const int64_t env = all ? (int64_t)i : (int64_t)__ldcg(list + kListHeader + i % cap);
+        const uint32_t ep = __ldcg(st.episode + env);
+        WarpPhilox rng;
+        uint32_t des, cells[9];
+        reset_sample(cfg, st, env, rng, ep, des, cells);
+        reset_record_write(st.reset_rec + env * 8, ep, des, cells);
+    }
+}
+
 // one thread per world, K steps per launch (K = 1: cw_step; K > 1: cw_rollout).  `obs` (nullable): the world's device frame is
 // kept current by render_edit.  CW_F_DEFER_RESET: a finished world is counted and reported but NOT re-seeded here (the caller
-// follows up with a masked cw_reset, which also renders the new episode's frames).
+// follows up with a masked cw_reset, which also renders the new episode's frames).  CTAs >= step_blocks are refill CTAs (above).
+#ifndef CW_STEP_MINBLOCKS
+#define CW_STEP_MINBLOCKS 6   /* <= 80 registers: 512 stepping + up to 376 refill CTAs of a 65536-world launch fit one wave */
+#endif
 template <bool kEdit>   // (a separate instantiation: the frame patching must not cost the compact path registers)
-__global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
+__global__ void __launch_bounds__(128, CW_STEP_MINBLOCKS) cw_step_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
                                                       int32_t* __restrict__ reward, uint8_t* __restrict__ done,
-                                                      unsigned long long* stats, uint8_t* obs, uint32_t* list, int K, int flags) {
+                                                      unsigned long long* stats, uint8_t* obs, uint32_t* list, int K, int flags,
+                                                      int step_blocks) {
     CW_WSTAMP(0);
     pdl_launch_dependents();
     pdl_wait();
     CW_WSTAMP(1);
+    const bool records = !kEdit && st.reset_rec != nullptr;
+    if (!kEdit && (int)blockIdx.x >= step_blocks) {               // refill CTAs: the draws of the resets queued by the previous launch
+        reset_refill(cfg, st, (int64_t)(blockIdx.x - step_blocks) * 4 + (threadIdx.x >> 5), (int64_t)(gridDim.x - step_blocks) * 4,
+                     step_blocks == 0);
+    } else {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = n < st.n;
     const int64_t nn = valid ? n : 0;
@@ -470,6 +511,7 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
     const uint8_t* ig = st.init_grid + nn * cfg.cell_stride;
     uint32_t agent = 0, goal = 0, ep = 0;
     int t = 0;
+    bool queued = false;                                          // this world is already in the refill queue of this launch
     if (valid) { agent = st.agent[n]; goal = st.goal[n]; t = st.t[n]; ep = ((flags & CW_F_AUTO_RESET) && !(flags & CW_F_DEFER_RESET)) ? st.episode[n] : 0u; }
     for (int k = 0; k < K; k++) {
         bool dn = false;
@@ -499,21 +541,62 @@ __global__ void __launch_bounds__(128) cw_step_kernel(const CwConfig cfg, const 
 #ifdef CW_TIMING
             if (g_dbg && (threadIdx.x & 31) == 0) g_dbg[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16 + 9] = __popc(m);
 #endif
+            uint32_t q = 0, qbase = 0;
+            if (records && m) {                                   // queue them for the refill CTAs of the next launch (once per launch);
+                q = __ballot_sync(0xffffffffu, valid && dn && !queued);   // the atomic is issued now, its result used after the re-seeding
+                if (q && lane_id() == __ffs(q) - 1) qbase = atomicAdd(st.reset_list, (uint32_t)__popc(q));
+            }
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
                 const int64_t env = __shfl_sync(0xffffffffu, n, src);
                 const uint32_t env_ep = __shfl_sync(0xffffffffu, ep, src);
-                WarpPhilox rng;
                 uint32_t ag, gl;
-                reset_warp(cfg, st, env, nullptr, rng, ag, gl, env_ep);
+                bool fast = false;
+                if (records) {
+                    // lanes 0 / 1 fetch one 16-byte half each (L2); the record is used only if BOTH halves carry this episode's tag
+                    const int lane = lane_id();
+                    uint4 h = make_uint4(env_ep, 0u, 0u, 0u);
+                    if (lane < 2) h = __ldcg(reinterpret_cast<const uint4*>(st.reset_rec + env * 8) + lane);
+                    fast = __all_sync(0xffffffffu, h.x == env_ep);
+                    if (fast) {
+                        const uint32_t a1 = __shfl_sync(0xffffffffu, h.y, 0), a2 = __shfl_sync(0xffffffffu, h.z, 0), a3 = __shfl_sync(0xffffffffu, h.w, 0);
+                        const uint32_t b1 = __shfl_sync(0xffffffffu, h.y, 1), b2 = __shfl_sync(0xffffffffu, h.z, 1);
+                        const uint32_t cells[9] = {a2 & 0xFFFFu, a2 >> 16, a3 & 0xFFFFu, a3 >> 16, b1 & 0xFFFFu, b1 >> 16, b2 & 0xFFFFu, b2 >> 16, a1 >> 16};
+                        reset_apply(cfg, st, env, nullptr, a1 & 0xFFFFu, cells, env_ep, ag, gl);
+                    }
+                }
+                if (!fast) {
+                    WarpPhilox rng;
+                    reset_warp(cfg, st, env, nullptr, rng, ag, gl, env_ep);
+                }
                 if (lane_id() == src) { agent = ag; goal = gl; t = 0; ep = env_ep + 1; if (st.init_agent) st.init_agent[env] = ag; }
+            }
+            if (q) {
+                qbase = __shfl_sync(0xffffffffu, qbase, __ffs(q) - 1);
+                if (valid && dn && !queued) {
+                    st.reset_list[kListHeader + (qbase + __popc(q & ((1u << lane_id()) - 1u))) % (2u * (uint32_t)st.n)] = (uint32_t)n;
+                    queued = true;
+                }
             }
         }
     }
     CW_WSTAMP(3);
     if (valid) { st.agent[n] = agent; st.goal[n] = goal; st.t[n] = t; }
     CW_WSTAMP(4);
+    }
+    if (records) {                                                // the last CTA out advances the queue window for the next launch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            uint32_t* l = st.reset_list;
+            if (atomicAdd(l + 3, 1u) == gridDim.x - 1) {
+                if (step_blocks == 0) { l[0] = 0; l[1] = 0; l[2] = 0; }          // prefill: every record is fresh, the queue empty
+                else { l[2] = l[1]; l[1] = *reinterpret_cast<volatile uint32_t*>(l); }
+                l[3] = 0;
+            }
+        }
+    }
 }
 
 // Delta transport (cw_step_delta): one thread per world, records straight into (possibly host-mapped) memory.  The step of a
@@ -901,6 +984,7 @@ struct Tunables {
     int bands_per_chunk = env_int("CW_BANDS_PER_CHUNK", 0), chunk_bytes = env_int("CW_CHUNK_BYTES", 25 * 1024);
     int frame_buffers = env_int("CW_FRAME_BUFFERS", 0), first_split = env_int("CW_FIRST_SPLIT", 4);
     int ctas_per_sm = env_int("CW_CTAS_PER_SM", 0), group = env_int("CW_GROUP", 0);
+    int refill_ctas = env_int("CW_REFILL_CTAS", 0);             // experiment: cap on the refill CTAs of the compact step launch
     int no_chain = env_int("CW_NO_CHAIN", 0);                   // 1: cw_step_render_chained degrades to ordinary launches
     int chain_timeout_ms = env_int("CW_CHAIN_TIMEOUT_MS", 0);   // > 0: spin limit of the chain waits
 };
@@ -1016,6 +1100,11 @@ static int check_state(const CwState* st) {
     return 0;
 }
 
+// pre-drawn reset records apply to auto-resetting launches of worlds without a fixed pool, when the caller provides both buffers
+static bool reset_records_usable(const CwState* st, int flags) {
+    return st->reset_rec && st->reset_list && st->n_fixed == 0 && (flags & CW_F_AUTO_RESET) && st->n <= 0x3FFFFFFF;
+}
+
 int step_render_chained_notify(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
                                uint8_t* obs, uint8_t* goal_obs, uint8_t* init_obs, int64_t* stats, int flags, uint32_t* chain,
                                int chain_pos, int obs_ring, uint8_t* status, void* stream) {
@@ -1089,8 +1178,34 @@ int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, i
     if (st->n == 0 || K == 0) return 0;
     if (!actions) return CW_E_NULLPTR;
     const int64_t blocks = (st->n + 127) / 128;
-    cudaError_t le = launch_pdl(cw_step_kernel<false>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions,
-                                reward, done, (unsigned long long*)stats, (uint8_t*)nullptr, (uint32_t*)nullptr, K, flags);
+    int64_t refill = 0;
+    CwState s2 = *st;
+    if (reset_records_usable(st, flags)) {                        // refill CTAs beside the stepping ones
+        DeviceInfo* dev;
+        rc = device_info(&dev); if (rc) return rc;
+        refill = blocks < (int64_t)dev->sms * 2 ? blocks : (int64_t)dev->sms * 2;   // (stepping + refill CTAs of a 65536-world launch: one wave)
+        if (tunables().refill_ctas > 0 && tunables().refill_ctas < refill) refill = tunables().refill_ctas;
+    } else {
+        s2.reset_rec = nullptr; s2.reset_list = nullptr;
+    }
+    cudaError_t le = launch_pdl(cw_step_kernel<false>, dim3((unsigned)(blocks + refill)), dim3(128), 0, (cudaStream_t)stream, *cfg, s2, actions,
+                                reward, done, (unsigned long long*)stats, (uint8_t*)nullptr, (uint32_t*)nullptr, K, flags, (int)blocks);
+    return (int)(le != cudaSuccess ? le : cudaGetLastError());
+}
+
+int cw_prefill_resets(const CwConfig* cfg, const CwState* st, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    rc = check_reset_config(cfg); if (rc) return rc;
+    rc = check_state(st); if (rc) return rc;
+    if (st->n == 0) return 0;
+    if (!reset_records_usable(st, CW_F_AUTO_RESET)) return CW_E_NULLPTR;
+    DeviceInfo* dev;
+    rc = device_info(&dev); if (rc) return rc;
+    const int64_t want = (st->n + 3) / 4;                         // one warp per world, at most a few waves
+    const int64_t blocks = want < (int64_t)dev->sms * 16 ? want : (int64_t)dev->sms * 16;
+    cudaError_t le = launch_pdl(cw_step_kernel<false>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, (const uint8_t*)nullptr,
+                                (int32_t*)nullptr, (uint8_t*)nullptr, (unsigned long long*)nullptr, (uint8_t*)nullptr, (uint32_t*)nullptr, 0,
+                                CW_F_AUTO_RESET, 0);
     return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
 
@@ -1107,7 +1222,7 @@ int cw_step_render_edit(const CwConfig* cfg, const CwState* st, const uint8_t* a
     const int64_t blocks = (st->n + 127) / 128;
     cudaError_t le = launch_pdl(cw_step_kernel<true>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, *cfg, *st, actions,
                                 reward, done, (unsigned long long*)stats, obs, scratch, 1,
-                                flags | ((flags & CW_F_AUTO_RESET) ? CW_F_DEFER_RESET : 0));
+                                flags | ((flags & CW_F_AUTO_RESET) ? CW_F_DEFER_RESET : 0), (int)blocks);
     if (le != cudaSuccess) return (int)le;
     if (!(flags & CW_F_AUTO_RESET)) return (int)cudaGetLastError();
     EnvArgs a = {};                                               // reset of the queued worlds + their three frames, one world per CTA

@@ -209,6 +209,12 @@ class BatchedCraftingWorldEnv:
         if obs_mode == "onehot":                  # compact imagined goal state (one-hot family)
             self.goal_grid = torch.zeros((N, stride), dtype=torch.uint8, device=dev)
             self.goal_agent = torch.zeros(N, dtype=torch.int32, device=dev)
+        # compact step path: pre-drawn reset records + their refill queue (cw_prefill_resets; include/cw_b200.h CwState)
+        self.reset_rec = self.reset_list = None
+        if obs_mode == "compact" and self.auto_reset and not self.fixed_init_state and self.num_envs <= 0x3FFFFFFF:
+            self.reset_rec = torch.zeros((N, 8), dtype=torch.int32, device=dev)
+            self.reset_list = torch.zeros(4 + 2 * N, dtype=torch.int32, device=dev)
+        self._records_fresh = False
         self._obs_version = 0
         self._chain = None                        # chain words of cw_step_render_chained (allocated on first use)
         self._edit_scratch = None                 # work list of cw_step_render_edit (allocated on first use)
@@ -226,6 +232,7 @@ class BatchedCraftingWorldEnv:
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little") >> 1
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._records_fresh = False               # pre-drawn resets belong to the old key
         if self.fixed_init_state:
             self._generate_fixed_states(self.fixed_init_state)
         self._refresh_state_struct()
@@ -241,6 +248,7 @@ class BatchedCraftingWorldEnv:
         else:
             s.fixed_grid, s.fixed_agent, s.n_fixed = None, None, 0
         s.goal_grid, s.goal_agent, s.init_agent = self._ptr(self.goal_grid), self._ptr(self.goal_agent), self._ptr(self.init_agent)
+        s.reset_rec, s.reset_list = self._ptr(getattr(self, "reset_rec", None)), self._ptr(getattr(self, "reset_list", None))
 
     def _generate_fixed_states(self, n):
         """``generate_fixed_states`` (``ray.py:149-154``): pre-sample ``n`` worlds with ``sample_state``."""
@@ -252,7 +260,7 @@ class BatchedCraftingWorldEnv:
         pool.grid, pool.init_grid, pool.agent, pool.goal = g.data_ptr(), ig.data_ptr(), ag.data_ptr(), gl.data_ptr()
         pool.t, pool.episode, pool.n, pool.seed, pool.env_id_base = t.data_ptr(), ep.data_ptr(), n, self._seed, FIXED_POOL_ID_BASE
         pool.n_fixed = 0
-        pool.goal_grid = pool.goal_agent = pool.init_agent = None
+        pool.goal_grid = pool.goal_agent = pool.init_agent = pool.reset_rec = pool.reset_list = None
         with torch.cuda.device(self.device):
             _lib.check(self._lib.cw_reset(C.byref(self.cfg), C.byref(pool), None, None, None, None, self._stream()), "cw_reset(pool)")
         self._fixed_grid, self._fixed_agent = g, ag
@@ -355,9 +363,17 @@ class BatchedCraftingWorldEnv:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.cw_reset(C.byref(self.cfg), C.byref(self._state), self._ptr(m), self._ptr(self.obs),
                                           self._ptr(self.desired_goal), self._ptr(self.init_obs), self._stream()), "cw_reset")
+        self._prefill_resets()
         self._is_reset = True
         self._obs_version += 1
         return self._observation()
+
+    def _prefill_resets(self):
+        """Draw every world's NEXT reset ahead of time (compact step path); a no-op without the record buffers."""
+        if self.reset_rec is not None:
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.cw_prefill_resets(C.byref(self.cfg), C.byref(self._state), self._stream()), "cw_prefill_resets")
+        self._records_fresh = True
 
     def _as_actions(self, actions):
         a = actions
@@ -390,6 +406,8 @@ class BatchedCraftingWorldEnv:
         a = self._as_actions(actions)
         if a.shape != (self.num_envs,):
             raise ValueError(f"actions must have shape ({self.num_envs},), got {tuple(a.shape)}")
+        if not self._records_fresh:
+            self._prefill_resets()
         if chain_pos is not None and (self.obs_mode != "pixels" or not 0 <= int(chain_pos) < _lib.CHAIN_MAX_POS):
             raise ValueError(f"chain_pos needs obs_mode='pixels' and 0 <= chain_pos < {_lib.CHAIN_MAX_POS}")
         flags = _lib.F_AUTO_RESET if self.auto_reset else 0
@@ -453,6 +471,8 @@ class BatchedCraftingWorldEnv:
         if a.dim() != 2 or a.shape[1] != self.num_envs:
             raise ValueError(f"actions must have shape (K, {self.num_envs})")
         K = a.shape[0]
+        if not self._records_fresh:
+            self._prefill_resets()
         rew = dn = None
         if return_trace:
             rew = torch.empty((K, self.num_envs), dtype=torch.int32, device=self.device)

@@ -100,6 +100,13 @@ typedef struct CwState {
     uint8_t* goal_grid;   /* uint8 [N][cell_stride]: imagine_obs final_state, object codes */
     uint32_t* goal_agent; /* uint32[N]: agent word of the imagined state */
     uint32_t* init_agent; /* uint32[N]: agent word at reset (INIT_OBS_VECTOR's agent channel) */
+    /* optional, compact step path (cw_step / cw_rollout with CW_F_AUTO_RESET, no fixed pool): pre-drawn reset records.  What a
+     * reset draws depends only on (seed, global id, episode), so it is drawn ahead of time by extra CTAs of the step launches and
+     * a finished world is re-seeded by a copy instead of the Philox sampling (results are bit-identical; a missing / stale record
+     * falls back to the inline draw).  Both nullable (then every reset draws inline); zero both once, then call
+     * cw_prefill_resets after every cw_reset / change of seed. */
+    uint32_t* reset_rec;  /* uint32[N][8], 32-byte aligned: two 16-byte halves, each {episode tag, ...placement} (see cw_kernels.cu) */
+    uint32_t* reset_list; /* uint32[4 + 2N]: queue of worlds whose next record is due (tail, limit, head, ticket, ring) */
 } CwState;
 
 int cw_abi_version(void);
@@ -180,6 +187,10 @@ int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions
  * Same per-step semantics as cw_step. */
 int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
                int64_t* stats, int K, int flags, void* stream);
+
+/* Draw the NEXT reset of every world into st->reset_rec (one warp per world) and empty st->reset_list: call after cw_reset,
+ * cw_host-style state injection that changes episode counters, or a change of seed.  Needs both buffers and n_fixed == 0. */
+int cw_prefill_resets(const CwConfig* cfg, const CwState* st, void* stream);
 
 /* imagine_obs on the CURRENT state (ray.py:220-299) without resetting: goal image of each world using the stream
  * (seed, global id, episode[n]).  For states injected with load_state. */

@@ -51,7 +51,7 @@ def test_library_is_native_sm100a_with_tma_bulk_store():
 def test_struct_layout_matches_header(lib):
     from gym_craftingworld_b200 import _lib
     assert C.sizeof(_lib.CwConfig) == 8 * 4 + 16
-    assert C.sizeof(_lib.CwState) == 6 * 8 + 3 * 8 + 3 * 8 + 3 * 8
+    assert C.sizeof(_lib.CwState) == 6 * 8 + 3 * 8 + 3 * 8 + 3 * 8 + 2 * 8
 
 
 def test_argument_errors_are_codes_not_crashes(lib):

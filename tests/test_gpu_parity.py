@@ -659,3 +659,43 @@ def test_host_api_unbound_pageable_buffers_and_delta_rules(cw):
         o_rew, o_dn = ob.step_full(a, auto_reset=True, obs=o_obs)
         assert np.array_equal(rew, o_rew) and np.array_equal(dn, o_dn) and np.array_equal(frames, o_obs)
         _lib.check(lib.cw_host_destroy(h))
+
+
+@pytest.mark.parametrize("max_steps", [1, 2, 7])
+def test_compact_step_with_predrawn_reset_records_matches_oracle(cw, max_steps):
+    """cw_step / cw_rollout with pre-drawn reset records (CwState.reset_rec / reset_list): finished worlds are re-seeded by a copy
+    of a record drawn ahead of time by refill CTAs.  Episodes of 1 or 2 steps make every world finish (almost) every step, so
+    records are consumed while their successors are still being drawn -- the stale-tag fallback and the fast path must both
+    give the oracle's bits, step by step and inside multi-step rollouts, and after a change of seed."""
+    N, size, seed = 5000, 6, 31
+    env = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=seed, obs_mode="compact")
+    assert env.reset_rec is not None
+    ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed)
+    env.reset(); ob.reset()
+    rng = np.random.RandomState(6)
+    for k in range(40):
+        a = rng.randint(0, 6, N).astype(np.uint8)
+        _, reward, done, _ = env.step(torch.from_numpy(a).cuda())
+        o_reward, o_done = ob.step_full(a, auto_reset=True)
+        assert np.array_equal(reward.cpu().numpy(), o_reward) and np.array_equal(done.cpu().numpy(), o_done.astype(bool)), k
+    assert_env_equals_oracle(env, ob, f"single steps, max_steps {max_steps}")
+    if max_steps == 7:                                             # the records run one episode ahead of (nearly) every world
+        tags = env.reset_rec[:, 0].cpu().numpy().astype(np.uint32)
+        assert (tags == env.episode.cpu().numpy().astype(np.uint32)).mean() > 0.7
+    tape = rng.randint(0, 6, (33, N)).astype(np.uint8)            # several finishes per world inside ONE launch
+    rew, dn = env.rollout(torch.from_numpy(tape).cuda())
+    for k in range(33):
+        o_reward, o_done = ob.step_full(tape[k], auto_reset=True)
+        assert np.array_equal(rew[k].cpu().numpy(), o_reward) and np.array_equal(dn[k].cpu().numpy(), o_done.astype(bool)), k
+    assert_env_equals_oracle(env, ob, f"rollout, max_steps {max_steps}")
+    assert np.array_equal(env.stats.cpu().numpy(), ob.stats)
+    # a new key: the records drawn under the old one must not be used
+    env.seed(seed + 1)
+    ob2 = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed + 1)
+    ob2.grid[:] = ob.grid; ob2.init_grid[:] = ob.init_grid; ob2.agent[:] = ob.agent; ob2.goal[:] = ob.goal; ob2.t[:] = ob.t
+    ob2.episode[:] = ob.episode
+    for k in range(10):
+        a = rng.randint(0, 6, N).astype(np.uint8)
+        env.step(torch.from_numpy(a).cuda())
+        ob2.step_full(a, auto_reset=True)
+    assert_env_equals_oracle(env, ob2, "after seed()")

@@ -1,6 +1,7 @@
 """Experiment (needs ab/lib_timing.so built with -DCW_TIMING and CW_LIB_PATH pointing at it): per-CTA timeline of
 cw_env_kernel at config 2 in steady state (episodes desynchronised)."""
 import ctypes as C, os, sys
+sys.path.insert(0, ".")
 import numpy as np, torch
 import gym_craftingworld_b200 as cw
 from gym_craftingworld_b200 import _lib
