@@ -7,7 +7,8 @@ A "step" is one pass of the hot path over one batch of worlds: ONE fused step + 
 (cw_env_kernel) per step for the pixel workloads, one cw_step_kernel launch for the compact workload.  Worlds are
 sharded over ranks by global id with no data-path collective (weak scaling: per-GPU batch fixed); with N > 1 the
 24 x int64 episode-statistics vector is snapshotted on the step stream and all-reduced over NCCL on a side stream at
-every graph-replay boundary (every 128 steps, and once per timed window when K < 128), inside the timed region.
+every graph-replay boundary (every 128 steps, and once per timed window when K < 128): the reduction of the statistics
+up to step k overlaps steps k+1.., and the timed window only closes once it has finished.
 
 Prints ONE JSON line (rank 0):
   value         device-resident throughput of `--workload` (default cfg2 = BASELINE.json configs[1]): exactly K steps
@@ -249,6 +250,12 @@ class Ctx:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.stream = torch.cuda.Stream(device=self.dev)
+        import gym_craftingworld_b200 as cw
+        fair = max(1, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        bound = cw.bind_to_gpu_numa_node(self.local_rank)         # host-side polling / patching next to the GPU's PCIe root
+        if bound:                                                 # the worker pool keeps its fair share of ALL cores (not of one node's)
+            os.environ.setdefault("CW_HOST_THREADS", str(min(16, fair)))
+        self.numa = f"bound to {len(bound)} CPUs of the GPU's NUMA node" if bound else "not changed (single node or unknown topology)"
 
     def barrier(self):
         if self.world > 1:
@@ -366,14 +373,16 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
             g_rem = capture(rem, body) if rem else None
 
             def enqueue():
+                # at every replay boundary: snapshot the statistics on this stream (they are those of the step just finished), hand
+                # the copy to NCCL on the side stream, carry on stepping -- the reduction overlaps the next replay
                 for _ in range(n_full):
+                    if reducer is not None:
+                        reducer.reduce_async()
                     g_full.replay()
-                    if reducer is not None:
-                        reducer.reduce_async()
                 if g_rem is not None:
-                    g_rem.replay()
                     if reducer is not None:
                         reducer.reduce_async()
+                    g_rem.replay()
                 if reducer is not None:
                     reducer.wait()                                # `stream` waits for the side stream: the all-reduce is inside the window
             return enqueue
@@ -411,9 +420,9 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
 
         def run_ss():
             for _ in range(Ks // TAPE):
-                g_ss.replay()
                 if reducer is not None:
                     reducer.reduce_async()
+                g_ss.replay()
             if reducer is not None:
                 reducer.wait()
         rs = cx.time_steps(run_ss, Ks, windows=3)
@@ -594,7 +603,8 @@ def run_ours(args):
                        "launch": main_rec["launch"], "l2": main_rec["l2"], "episodes": main_rec["episodes"],
                        "timing": "exactly K steps between two CUDA events on the launching stream, behind a ~0.3 ms device-side gate so that every "
                                  "launch is queued before the start event; median of len(windows_ms) such windows, each MAX over ranks",
-                       "parallelism": f"dp{cx.world} (worlds sharded by global id, no data-path collective)"},
+                       "parallelism": f"dp{cx.world} (worlds sharded by global id, no data-path collective)",
+                       "host_affinity_rank0": cx.numa},
             "windows_ms": main_rec["windows_ms"], "rank_ms": main_rec["rank_ms"], "stats_allreduce": main_rec["stats_allreduce"],
             "clocks": sampler.summary(t0, t1, t_load0) if sampler else None,
             "gpu_launches": main_rec["gpu_launches"],

@@ -11,9 +11,9 @@ from .env import (ACTION_NAMES, COLORS_N, MAX_STEPS, OBJECTS, PICKUPABLE, TASK_L
                   BatchedCraftingWorldEnv, BatchedCraftingWorldEnvFlat, BatchedCraftingWorldEnvOneHot,
                   BatchedCraftingWorldEnvAltObs, make_config)
 from .host_env import HostCraftingWorldEnv  # noqa: E402
-from .dist import StatsReducer, shard_range  # noqa: E402
+from .dist import StatsReducer, bind_to_gpu_numa_node, shard_range  # noqa: E402
 from .vector import CraftingWorldVectorEnv, GifRecorder, register_envs  # noqa: E402
 
-__all__ = ["BatchedCraftingWorldEnv", "BatchedCraftingWorldEnvFlat", "BatchedCraftingWorldEnvOneHot", "BatchedCraftingWorldEnvAltObs", "HostCraftingWorldEnv", "CraftingWorldVectorEnv", "GifRecorder", "register_envs", "StatsReducer", "shard_range", "make_config", "TASK_LIST",
+__all__ = ["BatchedCraftingWorldEnv", "BatchedCraftingWorldEnvFlat", "BatchedCraftingWorldEnvOneHot", "BatchedCraftingWorldEnvAltObs", "HostCraftingWorldEnv", "CraftingWorldVectorEnv", "GifRecorder", "register_envs", "StatsReducer", "shard_range", "bind_to_gpu_numa_node", "make_config", "TASK_LIST",
            "OBJECTS", "PICKUPABLE", "ACTION_NAMES", "COLORS_N", "MAX_STEPS"]
 __version__ = "0.1.0"

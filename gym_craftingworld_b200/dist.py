@@ -18,6 +18,42 @@ def shard_range(total: int, rank: int, world: int):
     return lo, hi - lo
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int, sysfs: str = "/sys"):
+    """Restrict this process (and the threads it creates later: the host transport's workers) to the CPUs of the NUMA node the GPU
+    hangs off, when the machine has more than one node and the process is allowed to run there.  The host-buffer API polls
+    and patches mapped pinned memory the GPU writes over PCIe; from the wrong socket every such access crosses the
+    inter-socket link.  Returns the CPU set bound to, or None when nothing was changed (single node, unknown topology,
+    empty intersection with the current affinity)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs, "bus/pci/devices", pci, "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, f"devices/system/node/node{node}/cpulist")) as f:
+            node_cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        target = node_cpus & allowed
+        if not target or target == allowed:
+            return None
+        os.sched_setaffinity(0, target)
+        return target
+    except Exception:  # noqa: BLE001  (no sysfs, no such attribute: leave the affinity alone)
+        return None
+
+
 class StatsReducer:
     """Periodic all-reduce of the episode statistics (backend-agnostic: NCCL on GPUs, gloo in the CPU tests).
 

@@ -169,3 +169,11 @@ def test_tools_and_entry_points_compile():
     assert len(files) >= 8
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_numa_binding_helper_parses_topology(tmp_path, monkeypatch):
+    """bind_to_gpu_numa_node: cpulist parsing, and a no-op (None) whenever the topology is unknown -- as here, without a GPU."""
+    from gym_craftingworld_b200 import dist
+    assert dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert dist._parse_cpulist("") == set()
+    assert dist.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
