@@ -7,8 +7,8 @@ A "step" is one pass of the hot path over one batch of worlds: ONE fused step + 
 (cw_env_kernel) per step for the pixel workloads, one cw_step_kernel launch for the compact workload.  Worlds are
 sharded over ranks by global id with no data-path collective (weak scaling: per-GPU batch fixed); with N > 1 the
 24 x int64 episode-statistics vector is snapshotted on the step stream and all-reduced over NCCL on a side stream at
-every graph-replay boundary (every 128 steps, and once per timed window when K < 128): the reduction of the statistics
-up to step k overlaps steps k+1.., and the timed window only closes once it has finished.
+a graph-replay boundary every 128 env steps (BASELINE config 4's cadence, counted across the timed windows): the
+reduction of the statistics up to step k overlaps steps k+1.., and the window it falls into only closes once it has finished.
 
 Prints ONE JSON line (rank 0):
   value         device-resident throughput of `--workload` (default cfg2 = BASELINE.json configs[1]): exactly K steps
@@ -373,16 +373,18 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
             g_rem = capture(rem, body) if rem else None
 
             def enqueue():
-                # at every replay boundary: snapshot the statistics on this stream (they are those of the step just finished), hand
-                # the copy to NCCL on the side stream, carry on stepping -- the reduction overlaps the next replay
+                # BASELINE config 4: all-reduce the statistics every 128 env steps.  At a replay boundary at which 128 more steps
+                # have accumulated (every replay of a full graph; every ~6th window when K = 20) the statistics are snapshotted
+                # on this stream, the copy goes to NCCL on the side stream and stepping carries on -- the reduction overlaps the
+                # next replay, and the timed window only closes once it has finished.
                 for _ in range(n_full):
-                    if reducer is not None:
-                        reducer.reduce_async()
                     g_full.replay()
-                if g_rem is not None:
                     if reducer is not None:
-                        reducer.reduce_async()
+                        reducer.step(TAPE)
+                if g_rem is not None:
                     g_rem.replay()
+                    if reducer is not None:
+                        reducer.step(rem)
                 if reducer is not None:
                     reducer.wait()                                # `stream` waits for the side stream: the all-reduce is inside the window
             return enqueue
@@ -398,8 +400,10 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
                    "L2; no flush needed)") if pixels else "state 65536 x ~0.9 KB; step kernel is latency bound",
                episodes=("kept dense: auto-reset off, worlds step past done as upstream allows" if wl["dense"] else
                          "episode clocks staggered uniformly over [0, max_steps): steady-state share of time-outs / re-seeds in every step"),
-               stats_allreduce=(f"{reducer.reductions} NCCL all-reduces of the 16x24 int64 statistics issued so far (one per graph replay), "
-                                "inside the timed windows") if reducer is not None else None)
+               stats_allreduce=({"every_env_steps": TAPE, "issued_so_far": reducer.reductions,
+                                 "note": "NCCL SUM all-reduce of the 16x24 int64 statistics snapshot, on a side stream, every 128 env steps "
+                                         "(BASELINE config 4's cadence) counted across the windows; each is issued at a graph-replay boundary "
+                                         "and joined before the window's stop event"} if reducer is not None else None))
     launch_s = ms / 1e3 / K
     achieved = B * N / launch_s / 1e9
     if pixels:
@@ -420,9 +424,9 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
 
         def run_ss():
             for _ in range(Ks // TAPE):
-                if reducer is not None:
-                    reducer.reduce_async()
                 g_ss.replay()
+                if reducer is not None:
+                    reducer.step(TAPE)
             if reducer is not None:
                 reducer.wait()
         rs = cx.time_steps(run_ss, Ks, windows=3)

@@ -91,7 +91,8 @@ __device__ __forceinline__ void chain_wait_ge(const uint32_t* p, uint32_t want) 
 #ifdef CW_TIMING
 __device__ unsigned long long* g_dbg = nullptr;   // [CTA][16] globaltimer stamps (experiments only)
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define CW_STAMP(slot) do { if (g_dbg && (threadIdx.x == 0 || (slot) >= 8) ) g_dbg[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+__device__ int g_dbg_per_pos = 0;                  // > 0: the stamps of chain position p go to rows [p * g_dbg_per_pos, ...) (timeline of a whole chain)
+#define CW_STAMP(slot) do { if (g_dbg && (threadIdx.x == 0 || (slot) >= 8) ) g_dbg[((size_t)dbg_row0 + blockIdx.x) * 16 + (slot)] = gtimer(); } while (0)
 #define CW_WSTAMP(slot) do { if (g_dbg && (threadIdx.x & 31) == 0) g_dbg[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16 + (slot)] = gtimer(); } while (0)
 #else
 #define CW_STAMP(slot) do { } while (0)
@@ -158,6 +159,9 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
 
     // Programmatic dependent launch: let the next launch in the stream start its prologue now, and do not touch
     // anything the previous launch wrote (state, frames) until it has fully completed.
+#ifdef CW_TIMING
+    const size_t dbg_row0 = (size_t)(args.chain ? args.chain_pos : 0) * (size_t)g_dbg_per_pos;
+#endif
     CW_STAMP(0);
     pdl_launch_dependents();
     if (tid < 9) s_lut[tid] = kColorLUT[tid];
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
             }
             __threadfence_block();                                // tiles / s_* written above are visible to the composers
 #ifdef CW_TIMING
-            if (tid == kComposeThreads && g_dbg) { int np = 0; for (int i = 0; i < G; i++) np += (s_flag[i] & FL_PENDING) ? 1 : 0; g_dbg[(size_t)blockIdx.x * 16 + 9] = np; }
+            if (tid == kComposeThreads && g_dbg) { int np = 0; for (int i = 0; i < G; i++) np += (s_flag[i] & FL_PENDING) ? 1 : 0; g_dbg[((size_t)dbg_row0 + blockIdx.x) * 16 + 9] = np; }
 #endif
             if (tid == kComposeThreads) CW_STAMP(8);
             bar_arrive(BAR_RESET_DONE, kEnvThreads);
@@ -900,10 +904,15 @@ __global__ void __launch_bounds__(128) cw_frame_policy_kernel(const uint4* __res
     for (int64_t w = blockIdx.x; w < n; w += gridDim.x) {
         const uint4* f = obs + (size_t)w * words16;
         uint32_t h = 0;
-        for (uint32_t i = threadIdx.x; i < words16; i += 128) {
-            const uint4 v = __ldcs(f + i);
-            const uint32_t k = 8u * i + 1u;                       // 2 * (4 i) + 1
-            h += v.x * k + v.y * (k + 2u) + v.z * (k + 4u) + v.w * (k + 6u);
+        for (uint32_t i0 = threadIdx.x; i0 < words16; i0 += 4 * 128) {   // four independent 16-byte loads in flight per thread
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = (i0 + 128u * u < words16) ? __ldcs(f + i0 + 128u * u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = 8u * (i0 + 128u * u) + 1u;     // 2 * (4 i) + 1
+                h += v[u].x * k + v[u].y * (k + 2u) + v[u].z * (k + 4u) + v[u].w * (k + 6u);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
@@ -1136,6 +1145,7 @@ int cw_abi_version(void) { return CW_ABI_VERSION; }
 
 #ifdef CW_TIMING
 int cw_debug_set_timing(void* dev_ptr) { return (int)cudaMemcpyToSymbol(cw::g_dbg, &dev_ptr, sizeof(void*)); }
+int cw_debug_set_timing_rows_per_position(int rows) { return (int)cudaMemcpyToSymbol(cw::g_dbg_per_pos, &rows, sizeof(int)); }
 #endif
 
 const char* cw_error_string(int code) {

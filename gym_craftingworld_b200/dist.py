@@ -78,7 +78,7 @@ class StatsReducer:
         self.stats, self.every, self.group, self.inline = stats, int(every), group, bool(inline)
         self._buf = [torch.zeros_like(stats), torch.zeros_like(stats)]
         self._cur = 0                       # buffer of the most recent reduction
-        self._steps = self.reductions = 0
+        self._steps = self._last = self.reductions = 0
         self._side = torch.cuda.Stream(device=stats.device) if stats.is_cuda else None
         self._done = [None, None]           # CUDA events: reduction into buffer i has finished
         self._work = None
@@ -87,11 +87,15 @@ class StatsReducer:
     def global_stats(self) -> torch.Tensor:
         return self._buf[self._cur]
 
-    def step(self):
-        """Call once per env step; launches the reduction every ``every`` steps."""
-        self._steps += 1
-        if self._steps % self.every == 0:
+    def step(self, n: int = 1):
+        """Call after ``n`` env steps (a single step, or a replayed CUDA graph of ``n``); launches a reduction whenever ``every``
+        more steps have accumulated.  Returns True when one was launched."""
+        self._steps += int(n)
+        if self._steps - self._last >= self.every:
+            self._last = self._steps
             self.reduce_async()
+            return True
+        return False
 
     def reduce_async(self):
         nxt = self._cur ^ 1
