@@ -248,6 +248,8 @@ static int collect_status(const uint8_t* status, int64_t n, int32_t max_steps, i
     const __m128i one = _mm_set1_epi8(1), two = _mm_set1_epi8(2), zero = _mm_setzero_si128();
     const __m128i hit = _mm_set1_epi32(max_steps + 1), minus1 = _mm_set1_epi32(-1);
     for (; w + 16 <= n; w += 16) {
+        // every line was invalidated by the device's writes: keep the next few on their way while this one is examined
+        if ((w & 63) == 0) { _mm_prefetch(reinterpret_cast<const char*>(status + w + 256), _MM_HINT_T0); _mm_prefetch(reinterpret_cast<const char*>(status + w + 512), _MM_HINT_T0); }
         __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(status + w));
         int drained = 0;
         while (_mm_movemask_epi8(v) != 0xFFFF) {                  // bit 7 of every byte = "written"
@@ -464,6 +466,7 @@ static int host_step_delta(CwHostEnv* e, const uint8_t* act_src, int32_t* reward
         for (int64_t it = 0; it < total + ndef; it++) {
             const bool second = it >= total;
             const int64_t w = second ? deferred[it - total] : lo + it;
+            if (!second && (w & 3) == 0) __builtin_prefetch(recs + w + 32);   // record lines (4 records each), 8 lines ahead of the scan
             if (!second && !nopatch && w + kAhead < hi) prefetch(w + kAhead);
             if (!ready(w)) {
                 if (!second && ndef < kMaxDeferred) { deferred[ndef++] = w; continue; }
@@ -545,7 +548,7 @@ static int host_steps_device(CwHostEnv* e, const uint8_t* act_host, bool act_map
     cudaStream_t s = e->streams[0];
     const int64_t n = e->st.n;
     const size_t stride = ((size_t)n + 63) & ~(size_t)63;
-    int rc = ensure_pinned(&e->h_status, &e->h_status_bytes, (size_t)K * stride + (act_mapped ? 0 : (size_t)K * n));
+    int rc = ensure_pinned(&e->h_status, &e->h_status_bytes, (size_t)K * stride + (act_mapped ? 0 : (size_t)K * n) + 1024);
     if (rc) return rc;
     memset(e->h_status, 0, (size_t)K * stride);
     const uint8_t* act_dev = act_host;                            // (UVA: a page-locked host address is valid on the device)

@@ -292,7 +292,9 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     if (args.reward) args.reward[e] = rew;
                     if (args.done) args.done[e] = dn ? 1 : 0;
                     if constexpr (!kList) {
-                        if (args.status) args.status[e] = (uint8_t)(0x80u | (rew == cfg.max_steps ? 2u : 0u) | (dn ? 1u : 0u));
+                        // st.wt: written THROUGH the L2 to system memory now -- a plain store of a partial sector can sit in L2 until
+                        // the frame stream evicts it or the grid ends, i.e. the host would see it when the launch is all but over
+                        if (args.status) __stwt(args.status + e, (uint8_t)(0x80u | (rew == cfg.max_steps ? 2u : 0u) | (dn ? 1u : 0u)));
                     }
                     if (dn && (mode & M_AUTO_RESET)) {
                         flag |= FL_PENDING;
