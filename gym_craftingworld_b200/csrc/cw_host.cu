@@ -166,6 +166,7 @@ struct CwHostEnv {
     uint8_t* h_status;                // pinned + mapped: [K][status_stride] status bytes (grown on demand), then [K][N] staged actions
     size_t h_status_bytes;
     int chain_pos;                    // position of the next launch in the open chain (0: the next launch opens one)
+    std::vector<uint8_t> pending_lines;   // scratch of collect_status: status lines not yet complete
     // delta transport (CW_F_DELTA_TRANSPORT)
     uint4* h_delta;                   // pinned + mapped: per-world delta records written by the kernel
     uint32_t* h_fresh;                // pinned + mapped: sparse records of re-seeded worlds
@@ -224,56 +225,77 @@ static int ensure_pinned(uint8_t** buf, size_t* have, size_t need) {
 }
 static int ensure_frame_staging(CwHostEnv* e) { return ensure_pinned(&e->h_frames, &e->h_frames_bytes, (size_t)e->st.n * e->frame_bytes); }
 
-// Wait for the status bytes of one step (uint8[n] in mapped pinned memory, zero before the launch; the kernel stores
-// 0x80 | success << 1 | done per world) and unpack them into the caller's reward / done arrays.  A watchdog on the stream
-// turns a failed launch into an error instead of a hang.
+// Wait for the status bytes of one step (mapped pinned memory, zero before the launch; the kernel stores 0x80 | success << 1 | done
+// per world, the host pre-sets the padding of the last 64-byte line) and unpack them into the caller's reward / done arrays.
+// The bytes do not arrive in order, and every line the device writes is invalidated in this core's cache: a scan that waits on
+// line after line pays one serialized miss per line (64 lines = ~5 us at 4096 worlds, measured).  So the lines are swept in blocks
+// -- prefetch the block's pending lines, then examine them; complete lines are unpacked and dropped, the rest stay for the next
+// sweep -- and the misses overlap.  A watchdog on the stream turns a failed launch into an error instead of a hang.
 static int collect_status(const uint8_t* status, int64_t n, int32_t max_steps, int32_t* reward, uint8_t* done, cudaStream_t s,
-                          double* t_first_us = nullptr) {
-    uint64_t spins = 0;
+                          uint8_t* pending, double* t_first_us = nullptr) {
     if (t_first_us) {                                             // (CW_HOST_TRACE) when does the first byte land?
+        uint64_t spins = 0;
         const auto t0 = std::chrono::steady_clock::now();
         while (!(*reinterpret_cast<const volatile uint8_t*>(status) & 0x80u) && spins++ < (1ull << 26)) cpu_relax();
         *t_first_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-        spins = 0;
     }
-    auto stalled = [&]() -> int {                                 // 0: keep polling
-        cpu_relax();
-        if ((++spins & 0xFFFF) != 0) return 0;
-        const cudaError_t q = cudaStreamQuery(s);
-        if (q == cudaErrorNotReady) return 0;
-        return (int)(q != cudaSuccess ? q : cudaErrorLaunchFailure);   // the stream drained and the byte never came
-    };
-    int64_t w = 0;
-#if defined(__SSE2__)
-    const __m128i one = _mm_set1_epi8(1), two = _mm_set1_epi8(2), zero = _mm_setzero_si128();
-    const __m128i hit = _mm_set1_epi32(max_steps + 1), minus1 = _mm_set1_epi32(-1);
-    for (; w + 16 <= n; w += 16) {
-        // every line was invalidated by the device's writes: keep the next few on their way while this one is examined
-        if ((w & 63) == 0) { _mm_prefetch(reinterpret_cast<const char*>(status + w + 256), _MM_HINT_T0); _mm_prefetch(reinterpret_cast<const char*>(status + w + 512), _MM_HINT_T0); }
-        __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(status + w));
-        int drained = 0;
-        while (_mm_movemask_epi8(v) != 0xFFFF) {                  // bit 7 of every byte = "written"
-            if (drained) return drained;                          // (one last look after the stream drained)
-            drained = stalled();
-            asm volatile("" ::: "memory");
-            v = _mm_load_si128(reinterpret_cast<const __m128i*>(status + w));
+    const int64_t nlines = (n + 63) / 64;
+    memset(pending, 1, (size_t)nlines);
+    int64_t remaining = nlines;
+    auto unpack_scalar = [&](int64_t w0, int64_t w1) {
+        for (int64_t w = w0; w < w1; w++) {
+            const uint8_t b = status[w];
+            done[w] = b & 1u;
+            reward[w] = (b & 2u) ? max_steps : -1;
         }
-        _mm_storeu_si128(reinterpret_cast<__m128i*>(done + w), _mm_and_si128(v, one));
-        const __m128i succ = _mm_cmpeq_epi8(_mm_and_si128(v, two), two);   // 0xFF where reward == max_steps
-        const __m128i lo = _mm_unpacklo_epi8(succ, succ), hi = _mm_unpackhi_epi8(succ, succ);
-        const __m128i m[4] = {_mm_unpacklo_epi16(lo, lo), _mm_unpackhi_epi16(lo, lo), _mm_unpacklo_epi16(hi, hi), _mm_unpackhi_epi16(hi, hi)};
-        for (int q = 0; q < 4; q++)                               // -1 + (max_steps + 1) where successful
-            _mm_storeu_si128(reinterpret_cast<__m128i*>(reward + w + 4 * q), _mm_add_epi32(minus1, _mm_and_si128(m[q], hit)));
-        (void)zero;
-    }
+    };
+    int drained = 0;
+    for (uint64_t sweeps = 1; remaining; sweeps++) {
+        for (int64_t b0 = 0; b0 < nlines; b0 += 32) {
+            const int64_t b1 = b0 + 32 < nlines ? b0 + 32 : nlines;
+            bool any = false;
+            for (int64_t l = b0; l < b1; l++)
+                if (pending[l]) { __builtin_prefetch(status + 64 * l); any = true; }
+            if (!any) continue;
+            for (int64_t l = b0; l < b1; l++) {
+                if (!pending[l]) continue;
+                const int64_t w0 = 64 * l, cnt = n - w0 < 64 ? n - w0 : 64;
+#if defined(__SSE2__)
+                const __m128i* p = reinterpret_cast<const __m128i*>(status + w0);
+                const __m128i v[4] = {_mm_load_si128(p), _mm_load_si128(p + 1), _mm_load_si128(p + 2), _mm_load_si128(p + 3)};
+                if ((_mm_movemask_epi8(v[0]) & _mm_movemask_epi8(v[1]) & _mm_movemask_epi8(v[2]) & _mm_movemask_epi8(v[3])) != 0xFFFF) continue;
+                if (cnt == 64) {
+                    const __m128i one = _mm_set1_epi8(1), two = _mm_set1_epi8(2);
+                    const __m128i hit = _mm_set1_epi32(max_steps + 1), minus1 = _mm_set1_epi32(-1);
+                    for (int c = 0; c < 4; c++) {
+                        _mm_storeu_si128(reinterpret_cast<__m128i*>(done + w0 + 16 * c), _mm_and_si128(v[c], one));
+                        const __m128i succ = _mm_cmpeq_epi8(_mm_and_si128(v[c], two), two);   // 0xFF where reward == max_steps
+                        const __m128i lo = _mm_unpacklo_epi8(succ, succ), hi = _mm_unpackhi_epi8(succ, succ);
+                        const __m128i m[4] = {_mm_unpacklo_epi16(lo, lo), _mm_unpackhi_epi16(lo, lo), _mm_unpacklo_epi16(hi, hi), _mm_unpackhi_epi16(hi, hi)};
+                        for (int q = 0; q < 4; q++)               // -1 + (max_steps + 1) where successful
+                            _mm_storeu_si128(reinterpret_cast<__m128i*>(reward + w0 + 16 * c + 4 * q), _mm_add_epi32(minus1, _mm_and_si128(m[q], hit)));
+                    }
+                } else {
+                    unpack_scalar(w0, w0 + cnt);
+                }
+#else
+                bool all = true;
+                for (int64_t w = w0; w < w0 + 64; w++) all &= (reinterpret_cast<const volatile uint8_t*>(status)[w] & 0x80u) != 0;
+                if (!all) continue;
+                unpack_scalar(w0, w0 + cnt);
 #endif
-    for (; w < n; w++) {
-        const volatile uint8_t* p = status + w;
-        int drained = 0;
-        while (!(*p & 0x80u)) { if (drained) return drained; drained = stalled(); }
-        const uint8_t b = *p;
-        done[w] = b & 1u;
-        reward[w] = (b & 2u) ? max_steps : -1;
+                pending[l] = 0;
+                remaining--;
+            }
+        }
+        if (!remaining) break;
+        if (drained) return drained;                              // (that was the last look after the stream drained)
+        asm volatile("" ::: "memory");
+        cpu_relax();
+        if ((sweeps & 0x3FFF) == 0) {
+            const cudaError_t q = cudaStreamQuery(s);
+            if (q != cudaErrorNotReady) drained = (int)(q != cudaSuccess ? q : cudaErrorLaunchFailure);   // the bytes are final now
+        }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     return 0;
@@ -551,6 +573,9 @@ static int host_steps_device(CwHostEnv* e, const uint8_t* act_host, bool act_map
     int rc = ensure_pinned(&e->h_status, &e->h_status_bytes, (size_t)K * stride + (act_mapped ? 0 : (size_t)K * n) + 1024);
     if (rc) return rc;
     memset(e->h_status, 0, (size_t)K * stride);
+    if ((size_t)n != stride)                                      // the padding of each row's last line counts as "written"
+        for (int k = 0; k < K; k++) memset(e->h_status + (size_t)k * stride + n, 0x80, stride - (size_t)n);
+    if (e->pending_lines.size() < stride / 64) e->pending_lines.resize(stride / 64);
     const uint8_t* act_dev = act_host;                            // (UVA: a page-locked host address is valid on the device)
     if (!act_mapped) { uint8_t* a = e->h_status + (size_t)K * stride; memcpy(a, act_host, (size_t)K * n); act_dev = a; }
     const auto t_begin = std::chrono::steady_clock::now();
@@ -577,7 +602,7 @@ static int host_steps_device(CwHostEnv* e, const uint8_t* act_host, bool act_map
     const auto t_launched = std::chrono::steady_clock::now();
     for (int k = 0; k < K; k++) {
         rc = collect_status(e->h_status + (size_t)k * stride, n, e->cfg.max_steps, reward_host + (size_t)k * n, done_host + (size_t)k * n, s,
-                            (e->trace && K == 1) ? &e->tr_first_byte : nullptr);
+                            e->pending_lines.data(), (e->trace && K == 1) ? &e->tr_first_byte : nullptr);
         if (rc) { e->chain_pos = 0; return rc; }
     }
     if (e->trace && K == 1) {
