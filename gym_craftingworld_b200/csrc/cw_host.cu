@@ -242,6 +242,17 @@ static int collect_status(const uint8_t* status, int64_t n, int32_t max_steps, i
     const int64_t nlines = (n + 63) / 64;
     memset(pending, 1, (size_t)nlines);
     int64_t remaining = nlines;
+    // Each status line receives several partial writes from the device; a core that keeps re-reading the line forces every one of
+    // them to take it back first.  So do not touch the lines while they fill: watch a single sentinel byte (the last world's),
+    // and only then sweep -- by then the other lines are complete or about to be.  (CW_HOST_NO_SENTINEL=1: sweep from the start.)
+    static const bool no_sentinel = getenv("CW_HOST_NO_SENTINEL") && *getenv("CW_HOST_NO_SENTINEL") == '1';
+    if (!no_sentinel) {
+        const volatile uint8_t* last = status + n - 1;
+        for (uint64_t spins = 1; !(*last & 0x80u); spins++) {
+            cpu_relax();
+            if ((spins & 0xFFFF) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;   // (the sweeps below sort it out)
+        }
+    }
     auto unpack_scalar = [&](int64_t w0, int64_t w1) {
         for (int64_t w = w0; w < w1; w++) {
             const uint8_t b = status[w];

@@ -7,10 +7,12 @@ import gym_craftingworld_b200 as cw
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+import os
+SIZE = int(os.environ.get("SIZE", "21"))
 stagger = (int(sys.argv[3]) if len(sys.argv) > 3 else 1) != 0
 acts = np.random.RandomState(0).randint(0, 6, (128, N)).astype(np.uint8)
 def make(variant):
-    env = cw.HostCraftingWorldEnv(N, size=(21, 21), seed=0, return_frames=variant != "device", transport="delta" if variant == "delta" else "frames")
+    env = cw.HostCraftingWorldEnv(N, size=(SIZE, SIZE), seed=0, return_frames=variant != "device", transport="delta" if variant == "delta" else "frames")
     env.reset()
     if stagger:
         env.load_state(t=np.random.RandomState(1).randint(0, 300, N))     # staggered episodes: a steady stream of re-seeds
