@@ -123,8 +123,21 @@ inline void patch_cell(uint8_t* frame, int W, int cell, int code, bool agent_her
 }
 // a whole host frame of a world that holds at most 8 objects (a re-seeded world or its imagined goal state, ray.py:442-486):
 // everything else is black, so the frame is one memset plus <= 9 cells
+// zero a frame that is almost certainly not in this core's cache with non-temporal stores: no read-for-ownership of the 330 lines
+inline void zero_frame(uint8_t* frame, size_t bytes) {
+#if defined(__SSE2__)
+    if ((reinterpret_cast<uintptr_t>(frame) & 15u) == 0 && (bytes & 15u) == 0) {
+        const __m128i z = _mm_setzero_si128();
+        __m128i* p = reinterpret_cast<__m128i*>(frame);
+        for (size_t i = 0; i < bytes / 16; i++) _mm_stream_si128(p + i, z);
+        _mm_sfence();                                             // before the cached stores of the cells that follow
+        return;
+    }
+#endif
+    memset(frame, 0, bytes);
+}
 inline void render_sparse(uint8_t* frame, int H, int W, const uint32_t* objs8, uint32_t agent) {
-    memset(frame, 0, (size_t)48 * H * W);
+    zero_frame(frame, (size_t)48 * H * W);
     const int acell = (int)(agent & 0xFF) * W + (int)((agent >> 8) & 0xFF), hold = (int)((agent >> 16) & 0xFF);
     int under = 0;
     for (int k = 0; k < 8; k++) {
