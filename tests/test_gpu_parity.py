@@ -560,7 +560,7 @@ def test_randomized_configurations_vs_oracle(cw):
             native.set_fixed_pool(None)
 
 
-@pytest.mark.parametrize("size,N,max_steps", [(21, 3000, 15), (7, 130, 5), (32, 700, 20)])
+@pytest.mark.parametrize("size,N,max_steps", [(21, 3000, 15), (7, 130, 5), (32, 700, 20), (5, 1, 3), (6, 65, 4)])
 def test_host_env_device_consumer_matches_oracle(cw, size, N, max_steps):
     """Device-consumer transport (return_frames=False): chained launches, reward / done land in mapped host memory and the
     call returns on ONE notification word, frames stay in HBM (two alternating buffers).  reward / done after every call and
@@ -699,3 +699,24 @@ def test_compact_step_with_predrawn_reset_records_matches_oracle(cw, max_steps):
         env.step(torch.from_numpy(a).cuda())
         ob2.step_full(a, auto_reset=True)
     assert_env_equals_oracle(env, ob2, "after seed()")
+
+
+def test_host_env_device_consumer_survives_chain_wrap(cw):
+    """More single steps than a chain has positions (CW_CHAIN_MAX_POS = 1024): the handle re-opens the chain and carries on."""
+    N, size, max_steps, seed = 96, 5, 9, 41
+    env = cw.HostCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=seed, return_frames=False)
+    ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed)
+    env.reset(); ob.reset()
+    o_obs = ob.render()
+    rng = np.random.RandomState(9)
+    acts = rng.randint(0, 6, (1100, N)).astype(np.uint8)
+    for k in range(1100):
+        _, reward, done, _ = env.step(acts[k])
+        o_reward, o_done = ob.step_full(acts[k], auto_reset=True, obs=o_obs)
+        assert np.array_equal(reward, o_reward) and np.array_equal(done, o_done.astype(bool)), k
+    obs, _, _, _ = env.step_many(acts[:300])                       # and an open-loop run across the next wrap
+    for k in range(300):
+        ob.step_full(acts[k], auto_reset=True, obs=o_obs)
+    assert np.array_equal(env.fetch_frames()[0], o_obs)
+    assert np.array_equal(env.stats(), ob.stats)
+    env.close()
