@@ -655,7 +655,8 @@ int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host
         if (!obs_host) return CW_E_BADCONFIG;
         return host_step_delta(e, act_src, reward_host, done_host, obs_host);
     }
-    if (!obs_host) return host_steps_device(e, act_src, true, reward_host, done_host, 1);
+    if (!obs_host)                                                // (the device reads through the array's device alias: for cudaHostRegister-ed
+        return host_steps_device(e, act_direct ? (const uint8_t*)e->b_actions.dev : act_src, true, reward_host, done_host, 1);   //  memory it may differ)
     // frames transport: every frame crosses PCIe; slices alternate between two streams so copies overlap kernels
     uint8_t* frames_dst = obs_host;
     const bool direct = device_alias(obs_host) != nullptr;
@@ -700,7 +701,8 @@ int cw_host_step_many(CwHostEnv* e, const uint8_t* actions_host, int K, int32_t*
     if (e->flags & CW_F_DELTA_TRANSPORT) return CW_E_BADCONFIG;   // (see cw_host_step)
     CK(cudaSetDevice(e->device));
     // open-loop run for a device consumer: K chained launches enqueued back to back, reward / done rows unpacked as they land
-    return host_steps_device(e, actions_host, device_alias(actions_host) != nullptr, reward_host, done_host, K);
+    const void* alias = device_alias(actions_host);
+    return host_steps_device(e, alias ? (const uint8_t*)alias : actions_host, alias != nullptr, reward_host, done_host, K);
 }
 
 int cw_host_stats(CwHostEnv* e, int64_t* stats_host) {
