@@ -7,9 +7,14 @@ import this package and fails loudly when its CUDA library is missing).
 
 Contents
 --------
-``ref_shim``     loads the UNMODIFIED reference (``/root/reference``) under a throw-away ``gym`` /
-                 ``matplotlib`` import shim.  Only usable in the builder container; used to generate the
-                 frozen golden traces under ``tests/golden/`` and for live differential tests.
+``ref_shim``     loads the UNMODIFIED reference (``/root/reference`` in the builder container, else its install
+                 under ``oracle/_ref``) under a throw-away ``gym`` / ``matplotlib`` import shim; used to generate
+                 the frozen golden traces under ``tests/golden/``, for live differential tests (CPU and GPU) and as
+                 the reference arm of ``bench.py``.
+``build_ref``    installs the unmodified reference package into ``oracle/_ref`` (pip, offline, ``--no-deps``;
+                 git-ignored, travels to the GPU box with the built ``.so`` files).
+``pyenv``        per-world env loops for the CPU-baseline legs: the reference's own class (``run_worker_reference``)
+                 and the Python/NumPy port of round 1 (``run_worker``).
 ``compact``      NumPy/pure-Python restatement of the reference algorithm on the compact state encoding
                  (SURVEY.md Appendix A); every function cites the reference file:line it follows.
 ``cw_oracle.c``  plain-C restatement of the same algorithm (fast enough to check 4096 envs x hundreds of
@@ -22,5 +27,6 @@ Parity pin: the reference ships no golden vectors or known-answer tests for this
 pinned against OUTPUTS OF THE REFERENCE ITSELF, run here: ``tests/golden/make_golden.py`` drives the
 unmodified reference and freezes its per-step grids / positions / held item / achieved vector / reward /
 done / pixels; ``tests/test_oracle_golden.py`` checks both restatements against those traces and
-``tests/test_oracle_live_reference.py`` re-runs the differential live whenever ``/root/reference`` exists.
+``tests/test_oracle_live_reference.py`` re-runs the differential live wherever the reference exists
+(``/root/reference`` or ``oracle/_ref``), and ``tests/test_gpu_live_reference.py`` steps the CUDA kernels beside it.
 """
