@@ -554,8 +554,11 @@ def e2e_legs(cx, name, K, tape):
     e2e = dict(res["device"])
     e2e["api"] = ("HostCraftingWorldEnv(return_frames=False).step -> cw_host_step(obs_host=NULL): every step the actions come from pinned HOST "
                   "memory and reward + done are back in HOST memory when the call returns (one status byte per world through mapped pinned "
-                  "memory, no stream synchronisation); the pixel frames are produced in HBM by the fused step+reset+render kernel (chained "
-                  "launches, two-to-four rotating frame buffers) for a device-side consumer -- the call a GPU policy loop makes. "
+                  "memory, no stream synchronisation); the pixel frames are produced in HBM for a device-side consumer (four rotating frame "
+                  "buffers) -- the call a GPU policy loop makes.  Batches of <= 16384 worlds run as a two-launch pipeline per step: a "
+                  "thread-per-world step launch (cw_step_snap_kernel: status bytes, live state, a state snapshot) on one stream and the "
+                  "render launch of that snapshot (cw_env_kernel<V_PIPE>) on another, linked by release/acquire words -- the step of "
+                  "call k+1 never waits for the frames of call k; larger batches use one fused chained launch per step. "
                   "tests/test_gpu_parity.py::test_host_env_device_consumer_matches_oracle")
     e2e["step_many_128"] = dict(res["device_many"], note="cw_host_step_many: 128 steps of an open-loop tape per library call (K chained launches, "
                                 "reward/done rows unpacked as they land)")

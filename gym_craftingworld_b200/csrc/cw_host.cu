@@ -180,6 +180,14 @@ struct CwHostEnv {
     size_t h_status_bytes;
     int chain_pos;                    // position of the next launch in the open chain (0: the next launch opens one)
     std::vector<uint8_t> pending_lines;   // scratch of collect_status: status lines not yet complete
+    // pipelined single steps of the device-consumer transport (small batches): step launch on `s_step`, render launch on streams[0]
+    bool pipe_ok;                     // the handle has the snapshot buffers (CW_HOST_PIPE=0 turns the path off)
+    bool pipe_active;                 // the last step went through the pipe (a switch to another path drains both streams first)
+    cudaStream_t s_step;
+    cw::PipeSnap snap[cw::kPipeSlots];
+    uint8_t* d_snap;                  // one allocation behind the slots
+    uint32_t* d_pipe_words;           // [kPipeSlots] slot-consumed words, then one epoch word per 32 worlds
+    uint32_t pipe_seq;                // number of the last pipelined step (never reset: the words on the device are compared with it)
     // delta transport (CW_F_DELTA_TRANSPORT)
     uint4* h_delta;                   // pinned + mapped: per-world delta records written by the kernel
     uint32_t* h_fresh;                // pinned + mapped: sparse records of re-seeded worlds
@@ -189,7 +197,7 @@ struct CwHostEnv {
     uint32_t seq;                     // sequence tag of the last delta step (1..63)
     bool nopatch;                     // CW_HOST_NOPATCH=1 (diagnostics only): consume the records, skip the frame patching
     bool trace;                       // CW_HOST_TRACE=1 (diagnostics only): phase times, printed at destroy
-    double tr_launch, tr_first, tr_total, tr_first_byte;   // accumulated microseconds: launch call, launch -> first record / flag seen, whole call
+    double tr_launch, tr_first, tr_total, tr_first_byte, tr_mid;   // accumulated microseconds: launch call, launch -> first record / flag seen, whole call
     uint64_t tr_steps;
 };
 
@@ -358,6 +366,25 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
     }
     TRY(cudaMalloc(&e->d_stats, CW_STATS_REPLICAS * CW_STATS_LEN * 8));
     TRY(cudaMalloc(&e->d_chain, chain_words * 4));
+    // pipelined single steps: worth it where a step is a latency problem (one CTA wave of frames), i.e. for small batches
+    const char* pipe_env = getenv("CW_HOST_PIPE");
+    e->pipe_ok = !(flags & CW_F_DELTA_TRANSPORT) && n <= 16384 && !(pipe_env && *pipe_env == '0');
+    const size_t pipe_words = (size_t)cw::kPipeSlots + (size_t)((n + 31) / 32);
+    if (e->pipe_ok) {
+        const size_t per_slot = 2 * gb + (size_t)n * sizeof(uint4);
+        TRY(cudaMalloc(&e->d_snap, per_slot * cw::kPipeSlots));
+        TRY(cudaMalloc(&e->d_pipe_words, pipe_words * 4));
+        if (!rc) {
+            TRY(cudaMemset(e->d_pipe_words, 0, pipe_words * 4));
+            for (int i = 0; i < cw::kPipeSlots; i++) {
+                uint8_t* base = e->d_snap + per_slot * i;         // (gb is a multiple of 16: every part stays 16-byte aligned)
+                e->snap[i].grid = base; e->snap[i].goal = base + gb; e->snap[i].meta = reinterpret_cast<uint4*>(base + 2 * gb);
+            }
+        }
+        int lo = 0, hi = 0;                                       // the step launches must never queue behind frame traffic
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        TRY(cudaStreamCreateWithPriority(&e->s_step, cudaStreamNonBlocking, hi));
+    }
     TRY(cudaMallocHost(&e->h_actions, n)); TRY(cudaMallocHost(&e->h_reward, n * 5));
     if (!rc) e->h_done = reinterpret_cast<uint8_t*>(e->h_reward) + n * 4;
     TRY(cudaMallocHost(&e->h_stats, CW_STATS_REPLICAS * CW_STATS_LEN * 8));
@@ -399,9 +426,20 @@ int cw_host_bind_actions(CwHostEnv* e, const uint8_t* actions_host) {
     return 0;
 }
 
+// a path other than the pipelined single step is about to touch the state: drain the pipe's two streams first
+static int leave_pipe(CwHostEnv* e) {
+    if (!e->pipe_active) return 0;
+    CK(cudaStreamSynchronize(e->s_step));
+    CK(cudaStreamSynchronize(e->streams[0]));
+    e->pipe_active = false;
+    e->chain_pos = 0;
+    return 0;
+}
+
 int cw_host_sync(CwHostEnv* e) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     CK(cudaSetDevice(e->device));
+    if (e->s_step) CK(cudaStreamSynchronize(e->s_step));
     CK(cudaStreamSynchronize(e->streams[0]));
     CK(cudaStreamSynchronize(e->streams[1]));
     return 0;
@@ -411,8 +449,10 @@ int cw_host_reset(CwHostEnv* e, uint8_t* obs_host, uint8_t* goal_obs_host) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     CK(cudaSetDevice(e->device));
     cudaStream_t s = e->streams[0];
+    int rc = leave_pipe(e);
+    if (rc) return rc;
     e->chain_pos = 0; e->cur = 0;
-    int rc = cw_reset(&e->cfg, &e->st, nullptr, e->d_obs[0], e->d_goal_obs, nullptr, s);
+    rc = cw_reset(&e->cfg, &e->st, nullptr, e->d_obs[0], e->d_goal_obs, nullptr, s);
     if (rc) return rc;
     const size_t total = (size_t)e->st.n * e->frame_bytes;
     if (obs_host) CK(cudaMemcpyAsync(obs_host, e->d_obs[0], total, cudaMemcpyDeviceToHost, s));       // (pageable targets are staged by the runtime)
@@ -427,6 +467,7 @@ int cw_host_load_state(CwHostEnv* e, const uint8_t* grid_host, const uint32_t* a
                        const int32_t* t_host, uint8_t* obs_host) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     CK(cudaSetDevice(e->device));
+    { int rc = leave_pipe(e); if (rc) return rc; }
     CK(cudaStreamSynchronize(e->streams[0])); CK(cudaStreamSynchronize(e->streams[1]));
     const int64_t n = e->st.n;
     const size_t gb = (size_t)n * e->cfg.cell_stride;
@@ -639,6 +680,57 @@ static int host_steps_device(CwHostEnv* e, const uint8_t* act_host, bool act_map
     return 0;
 }
 
+// device-consumer transport, ONE step of a small batch: two launches on two streams (cw_internal.h).  The step launch answers in
+// the time a thread-per-world kernel needs; the render launch of the same step follows on the frame stream and is waited for by
+// nobody but the snapshot slot's next user, kPipeSlots steps later.  The call returns when every status byte has landed.
+static int host_step_pipe(CwHostEnv* e, const uint8_t* act_host, const uint8_t* act_dev, int32_t* reward_host, uint8_t* done_host) {
+    const int64_t n = e->st.n;
+    const size_t stride = ((size_t)n + 63) & ~(size_t)63;
+    int rc = ensure_pinned(&e->h_status, &e->h_status_bytes, stride + 1024);
+    if (rc) return rc;
+    memset(e->h_status, 0, (size_t)n);
+    if ((size_t)n != stride) memset(e->h_status + n, 0x80, stride - (size_t)n);
+    if (e->pending_lines.size() < stride / 64) e->pending_lines.resize(stride / 64);
+    if (!e->pipe_active) {                                        // entering from another path: its launches own the live state
+        CK(cudaStreamSynchronize(e->streams[0]));
+        e->chain_pos = 0;
+        e->pipe_active = true;
+    }
+    const auto t_begin = std::chrono::steady_clock::now();
+    const uint32_t seq = ++e->pipe_seq;
+    if (seq == 0) return CW_E_BADCONFIG;                          // (2^32 steps on one handle)
+    const int slot = (int)(seq % cw::kPipeSlots);
+    uint32_t* words = e->d_pipe_words;
+    static const bool skip_render = getenv("CW_PIPE_SKIP_RENDER") && *getenv("CW_PIPE_SKIP_RENDER") == '1';   // (experiment: the step chain alone)
+    const uint32_t want = (seq > (uint32_t)cw::kPipeSlots && !skip_render) ? seq - (uint32_t)cw::kPipeSlots : 0u;
+    rc = cw::step_snap_launch(&e->cfg, &e->st, act_dev, act_host, e->h_status, &e->snap[slot], words + cw::kPipeSlots, seq, words + slot, want,
+                              e->d_stats, e->flags & CW_F_AUTO_RESET, e->s_step);
+    if (rc) return rc;
+    const auto t_mid = std::chrono::steady_clock::now();
+    if (!skip_render) {
+    e->cur = (e->cur + 1) % e->nring;
+    rc = cw::render_pipe_launch(&e->cfg, n, &e->snap[slot], e->d_obs[e->cur], e->d_goal_obs, e->d_chain, e->chain_pos, e->nring,
+                                words + cw::kPipeSlots, seq, words + slot, e->streams[0]);
+    if (rc) return rc;
+    e->chain_pos = (e->chain_pos + 1) % CW_CHAIN_MAX_POS;
+    }
+    const auto t_launched = std::chrono::steady_clock::now();
+    if (e->trace) e->tr_mid += std::chrono::duration<double, std::micro>(t_mid - t_begin).count();
+    static const bool open_loop = getenv("CW_PIPE_OPENLOOP") && *getenv("CW_PIPE_OPENLOOP") == '1';   // (experiment: GPU-side rate of the pipe)
+    if (!open_loop)
+    rc = collect_status(e->h_status, n, e->cfg.max_steps, reward_host, done_host, e->s_step, e->pending_lines.data(),
+                        e->trace ? &e->tr_first_byte : nullptr);
+    if (rc) return rc;
+    if (e->trace) {
+        const auto t_end = std::chrono::steady_clock::now();
+        e->tr_launch += std::chrono::duration<double, std::micro>(t_launched - t_begin).count();
+        e->tr_first += std::chrono::duration<double, std::micro>(t_end - t_launched).count();
+        e->tr_total += std::chrono::duration<double, std::micro>(t_end - t_begin).count();
+        e->tr_steps++;
+    }
+    return 0;
+}
+
 int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host, uint8_t* done_host, uint8_t* obs_host) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     if (!actions_host || !reward_host || !done_host) return CW_E_NULLPTR;
@@ -655,8 +747,12 @@ int cw_host_step(CwHostEnv* e, const uint8_t* actions_host, int32_t* reward_host
         if (!obs_host) return CW_E_BADCONFIG;
         return host_step_delta(e, act_src, reward_host, done_host, obs_host);
     }
-    if (!obs_host)                                                // (the device reads through the array's device alias: for cudaHostRegister-ed
-        return host_steps_device(e, act_direct ? (const uint8_t*)e->b_actions.dev : act_src, true, reward_host, done_host, 1);   //  memory it may differ)
+    if (!obs_host) {                                              // (the device reads through the array's device alias: for cudaHostRegister-ed
+        const uint8_t* act_dev = act_direct ? (const uint8_t*)e->b_actions.dev : act_src;                                        //  memory it may differ)
+        if (e->pipe_ok) return host_step_pipe(e, act_src, act_dev, reward_host, done_host);
+        return host_steps_device(e, act_dev, true, reward_host, done_host, 1);
+    }
+    { int rc = leave_pipe(e); if (rc) return rc; }
     // frames transport: every frame crosses PCIe; slices alternate between two streams so copies overlap kernels
     uint8_t* frames_dst = obs_host;
     const bool direct = device_alias(obs_host) != nullptr;
@@ -700,6 +796,7 @@ int cw_host_step_many(CwHostEnv* e, const uint8_t* actions_host, int K, int32_t*
     }
     if (e->flags & CW_F_DELTA_TRANSPORT) return CW_E_BADCONFIG;   // (see cw_host_step)
     CK(cudaSetDevice(e->device));
+    { int rc = leave_pipe(e); if (rc) return rc; }
     // open-loop run for a device consumer: K chained launches enqueued back to back, reward / done rows unpacked as they land
     const void* alias = device_alias(actions_host);
     return host_steps_device(e, alias ? (const uint8_t*)alias : actions_host, alias != nullptr, reward_host, done_host, K);
@@ -709,6 +806,7 @@ int cw_host_stats(CwHostEnv* e, int64_t* stats_host) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     if (!stats_host) return CW_E_NULLPTR;
     CK(cudaSetDevice(e->device));
+    if (e->pipe_active) CK(cudaStreamSynchronize(e->s_step));     // (the episode statistics are the step launches')
     CK(cudaMemcpyAsync(e->h_stats, e->d_stats, CW_STATS_REPLICAS * CW_STATS_LEN * 8, cudaMemcpyDeviceToHost, e->streams[0]));
     CK(cudaStreamSynchronize(e->streams[0]));
     for (int k = 0; k < CW_STATS_LEN; k++) {                     // sum the replicas
@@ -748,13 +846,15 @@ int cw_host_destroy(CwHostEnv* e) {
     if (!e || e->magic != CW_HOST_MAGIC) return CW_E_BADHANDLE;
     cudaSetDevice(e->device);
     if (e->trace && e->tr_steps)
-        fprintf(stderr, "cw_host trace: %llu calls; launch call(s) %.2f us, launch -> first record / all status bytes %.2f us (first byte %.2f us), whole call %.2f us\n",
-                (unsigned long long)e->tr_steps, e->tr_launch / e->tr_steps, e->tr_first / e->tr_steps, e->tr_first_byte / e->tr_steps, e->tr_total / e->tr_steps);
+        fprintf(stderr, "cw_host trace: %llu calls; launch call(s) %.2f us (first of two: %.2f us), launch -> first record / all status bytes %.2f us (first byte %.2f us), whole call %.2f us\n",
+                (unsigned long long)e->tr_steps, e->tr_launch / e->tr_steps, e->tr_mid / e->tr_steps, e->tr_first / e->tr_steps, e->tr_first_byte / e->tr_steps, e->tr_total / e->tr_steps);
+    if (e->s_step) cudaStreamSynchronize(e->s_step);
     if (e->streams[0]) cudaStreamSynchronize(e->streams[0]);     // neither fast path ends with a stream sync
     if (e->streams[1]) cudaStreamSynchronize(e->streams[1]);
     cudaFree(e->st.grid); cudaFree(e->st.init_grid); cudaFree(e->st.agent); cudaFree(e->st.goal); cudaFree(e->st.t);
     cudaFree(e->st.episode); cudaFree(e->d_actions); cudaFree(e->d_reward); for (int i = 0; i < 4; i++) cudaFree(e->d_obs[i]);
-    cudaFree(e->d_goal_obs); cudaFree(e->d_stats); cudaFree(e->d_chain);
+    cudaFree(e->d_goal_obs); cudaFree(e->d_stats); cudaFree(e->d_chain); cudaFree(e->d_snap); cudaFree(e->d_pipe_words);
+    if (e->s_step) cudaStreamDestroy(e->s_step);
     cudaFreeHost(e->h_actions); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_stats);
     if (e->h_status) cudaFreeHost(e->h_status);
     if (e->h_frames) cudaFreeHost(e->h_frames);

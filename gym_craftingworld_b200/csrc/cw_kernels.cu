@@ -58,6 +58,12 @@ struct EnvArgs {
     uint32_t* chain;         // [CW_CHAIN_MAX_POS] finished-CTA counters per chain position, then one epoch word per group
     int chain_pos;           // position of this launch in its chain (0 = ordinary launch that opens a chain)
     int chain_ring;          // the chain's frame buffers rotate with this period (>= 1)
+    // pipelined host transport (V_PIPE, cw_host.cu): render-only launch fed by the snapshots of cw_step_snap_kernel
+    const uint4* pmeta;      // [N] {agent, agent of the imagined goal state, flags, -} of the snapshot slot (rgrid = its grid rows)
+    const uint8_t* pgoal;    // [N][cell_stride] imagined goal state of the worlds re-seeded in this step
+    const uint32_t* pepoch;  // [ceil(N / 32)] one word per warp of the step launch: the step number it has published
+    uint32_t* pslot;         // the slot's "consumed" word: the last CTA out stores pseq (the step kernel waits for it before reuse)
+    uint32_t pseq;           // number of this step (1, 2, ...; compared modulo 2^32)
 };
 
 // ---- chained launches: acquire / release on the chain words (gpu scope), bounded spins --------------------------
@@ -89,15 +95,28 @@ __device__ __forceinline__ void chain_wait_ge(const uint32_t* p, uint32_t want) 
     }
 }
 
+// the same for a step NUMBER that may wrap: spin until *p has reached `want` (signed distance)
+__device__ __forceinline__ void chain_wait_seq(const uint32_t* p, uint32_t want) {
+    if ((int32_t)(ld_acquire_gpu(p) - want) >= 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        __nanosleep(64);
+        if ((int32_t)(ld_acquire_gpu(p) - want) >= 0) return;
+        if (global_timer_ns() - t0 > g_chain_timeout_ns) __trap();
+    }
+}
+
 #ifdef CW_TIMING
 __device__ unsigned long long* g_dbg = nullptr;   // [CTA][16] globaltimer stamps (experiments only)
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ int g_dbg_per_pos = 0;                  // > 0: the stamps of chain position p go to rows [p * g_dbg_per_pos, ...) (timeline of a whole chain)
 #define CW_STAMP(slot) do { if (g_dbg && (threadIdx.x == 0 || (slot) >= 8) ) g_dbg[((size_t)dbg_row0 + blockIdx.x) * 16 + (slot)] = gtimer(); } while (0)
 #define CW_WSTAMP(slot) do { if (g_dbg && (threadIdx.x & 31) == 0) g_dbg[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16 + (slot)] = gtimer(); } while (0)
+#define CW_SSTAMP(slot) do { if (g_dbg && (threadIdx.x & 31) == 0 && blockIdx.x < 400) g_dbg[((size_t)600 + blockIdx.x) * 16 + (slot)] = gtimer(); } while (0)
 #else
 #define CW_STAMP(slot) do { } while (0)
 #define CW_WSTAMP(slot) do { } while (0)
+#define CW_SSTAMP(slot) do { } while (0)
 #endif
 
 enum : int { FL_RENDER = 1, FL_FRESH = 2, FL_GOAL = 4, FL_PENDING = 8 /* reset warp has work on this world */ };
@@ -118,17 +137,21 @@ enum : int { BAR_COMPOSE = 1, BAR_RESET_DONE = 2 };
 // Three instantiations (V_PLAIN ordinary launch, V_CHAINED chain protocol, V_LIST work-list re-seed): separate code, so the
 // ordinary launch is exactly what it was -- the extra control flow measurably slowed it (6 % at 131072 worlds) when all
 // shared one kernel body.
-enum : int { V_PLAIN = 0, V_CHAINED = 1, V_LIST = 2 };
+// V_PIPE (pipelined host transport, section 3.6): a render-only member of a chain.  The state it renders is the SNAPSHOT a
+// cw_step_snap_kernel launch on another stream published (per 128 worlds, release / acquire), so it never waits for a grid and
+// nothing waits for it except the snapshot slot's next user and the frame buffer's next writer.
+enum : int { V_PLAIN = 0, V_CHAINED = 1, V_LIST = 2, V_PIPE = 3 };
 template <int kVariant>
 __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig cfg, const CwState st, const EnvArgs args) {
-    constexpr bool kChained = kVariant == V_CHAINED, kList = kVariant == V_LIST;
+    constexpr bool kChained = kVariant == V_CHAINED, kList = kVariant == V_LIST, kPipe = kVariant == V_PIPE;
+    constexpr bool kLinked = kChained || kPipe;                   // launches linked by dataflow: no whole-grid wait at the start
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_lut[9];
     __shared__ uint32_t s_agent[32], s_gagent[32], s_goal[32], s_ep[32];
     __shared__ uint32_t s_flag[32];
     __shared__ uint32_t s_obj[8];
     __shared__ uint32_t s_anypend;
-    __shared__ uint32_t s_pre[kVariant == V_CHAINED ? 5 : 1][32];              // chained: next group's scalars, parked by the reset warp
+    __shared__ uint32_t s_pre[kLinked ? 5 : 1][32];                            // chained: next group's scalars, parked by the reset warp
 
     const int H = cfg.H, W = cfg.W, cs = cfg.cell_stride;
     const int G = args.group, F = args.nbuf, mode = args.mode;
@@ -154,7 +177,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     // grids still COMPLETE in stream order.
     const uint32_t cpos = (uint32_t)args.chain_pos;
     constexpr bool chained = kChained;
-    const bool chain_follow = chained && cpos > 0;
+    const bool chain_follow = kLinked && cpos > 0;
     uint32_t* const c_fin = args.chain;
     uint32_t* const c_epoch = args.chain + CW_CHAIN_MAX_POS;
 
@@ -222,6 +245,27 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
         cp_async_commit();
     };
 
+    // Pipelined launches: the same division of labour; the group's worlds were published by the step launch's warps
+    // [e0 / 32, (e0 + cnt - 1) / 32] (one epoch word each; G <= 32: at most two), its tiles are rows of the snapshot.
+    auto prefetch_pipe = [&](int64_t g, int sgi) {                // reset warp only
+        const int lane = tid - kComposeThreads;
+        if (g < ngroups) {
+            const int64_t e0 = g * G;
+            const int cnt = (int)min((int64_t)G, st.n - e0);
+            const int64_t b0 = e0 >> 5, b1 = (e0 + cnt - 1) >> 5;
+            chain_wait_seq(args.pepoch + b0, args.pseq);
+            if (b1 != b0) chain_wait_seq(args.pepoch + b1, args.pseq);
+            const uint8_t* src = grid_in + e0 * cs;
+            uint8_t* dst = tiles + (size_t)sgi * G * cs;
+            for (int i = lane; i < cnt * nchunk16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+            if (lane < cnt) {
+                const uint4 m = __ldcg(args.pmeta + e0 + lane);
+                s_pre[0][lane] = m.x; s_pre[1][lane] = m.y; s_pre[2][lane] = m.z;
+            }
+        }
+        cp_async_commit();
+    };
+
     int slot = 0;                                                 // ring slot of the next frame chunk
     const int first_bands = max(1, (args.bands_per_chunk + args.first_split - 1) / args.first_split);
     // expand one world (tile `src`) into the ring and stream it to dst (and dst2 when non-null); compose warps only
@@ -243,9 +287,9 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     };
 
     int stage = 0;
-    if constexpr (kChained) {
+    if constexpr (kLinked) {
         if (!composer) {
-            prefetch_chained(blockIdx.x, 0);
+            if constexpr (kPipe) prefetch_pipe(blockIdx.x, 0); else prefetch_chained(blockIdx.x, 0);
             // frame buffers rotate with period chain_ring: the launch that last wrote the buffer this one is about to
             // write must have completed (all its CTAs counted).  With a ring >= 2 that launch is long gone; with a
             // single buffer this makes the launch wait for its predecessor like an ordinary one.
@@ -260,14 +304,14 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
         int c_t = p_t, c_a = p_a;
         const int c_forced = p_forced;
         const int64_t c_e0 = p_e0;
-        if constexpr (kChained) {
+        if constexpr (kLinked) {
             cp_async_wait<0>();                                   // (reset warp) this group's tiles have landed
         } else {
             prefetch(gi + gridDim.x, stage ^ 1);
             cp_async_wait<1>();                                   // everything but the newest group has landed
         }
         __syncthreads();
-        if constexpr (kChained) {
+        if constexpr (kLinked) {
             if (tid == 0 && gi == (int64_t)blockIdx.x) fence_proxy_async_all();   // orders the bulk stores after the acquire above
             if (tid < 32) { c_agent = s_pre[0][tid]; c_goal = s_pre[1][tid]; c_t = (int)s_pre[2][tid]; c_a = (int)s_pre[3][tid]; c_ep = s_pre[4][tid]; }
         }
@@ -285,6 +329,9 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                 if (!skip && (mode & M_RENDER)) flag |= FL_RENDER;
                 if ((mode & M_FORCE_RESET) && c_forced) flag |= FL_PENDING;
                 if (mode & M_IMAGINE_ONLY) flag |= FL_PENDING;
+                if constexpr (kPipe) {                            // c_goal / c_t carry the snapshot's goal-state agent word / flags
+                    if ((c_t & 1) && args.goal_obs) flag |= FL_PENDING;      // re-seeded in this step: its goal frame is due
+                }
                 if (mode & M_STEP) {
                     int t = c_t, wcell, wval;
                     bool dn;
@@ -305,7 +352,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     }
                 }
             }
-            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; s_ep[lane] = c_ep; }
+            if (lane < G) { s_agent[lane] = agent; s_goal[lane] = goal; s_flag[lane] = flag; s_ep[lane] = kPipe ? (uint32_t)c_t : c_ep; }
             const uint32_t pend = __ballot_sync(0xffffffffu, (flag & FL_PENDING) != 0);
             if (lane == 0) s_anypend = pend;
         }
@@ -323,6 +370,19 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                 if (!(flag & FL_PENDING)) continue;
                 const int64_t er = e0 + i;
                 uint8_t* tile = gt + i * cs;
+                if constexpr (kPipe) {
+                    // the imagined goal state was drawn by the step launch: fetch its tile.  The goal frames have no ring: if the
+                    // episode that just ended was shorter than the frame ring, the launch that wrote this world's previous goal
+                    // frame may still be running -- wait for those launches (1 .. length positions back) to complete first.
+                    uint8_t* im = simag + i * cs;
+                    for (int ch = lane; ch < nchunk16; ch += 32)
+                        reinterpret_cast<uint4*>(im)[ch] = __ldcg(reinterpret_cast<const uint4*>(args.pgoal + er * cs) + ch);
+                    const uint32_t len = s_ep[i] >> 8;
+                    for (uint32_t j = 1; j <= len && j < (uint32_t)args.chain_ring && j <= cpos; j++) chain_wait_ge(c_fin + (cpos - j), gridDim.x);
+                    if (lane == 0) { s_gagent[i] = s_goal[i]; s_flag[i] = flag | FL_GOAL; }
+                    __syncwarp();
+                    continue;
+                }
                 WarpPhilox rng;
                 uint32_t ag = s_agent[i], gl = s_goal[i];
                 if (!(mode & M_IMAGINE_ONLY)) {                   // reset(): ray.py:156-218
@@ -369,6 +429,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
             if (tid == kComposeThreads) CW_STAMP(8);
             bar_arrive(BAR_RESET_DONE, kEnvThreads);
             if constexpr (kChained) prefetch_chained(gi + gridDim.x, stage ^ 1);   // s_pre was consumed before this iteration's 2nd barrier
+            if constexpr (kPipe) prefetch_pipe(gi + gridDim.x, stage ^ 1);
         } else {
             // ---- C: expand + stream out: untouched worlds first, worlds from the reset warp after its arrival ------
             // the very first frame of the launch goes out in quarter-frame stores: the launch is bound by the DRAM
@@ -402,9 +463,10 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
     cp_async_wait<0>();
     if (tid == 0) {
         bulk_wait_all();
-        if (chained) {                                            // this CTA's frames of chain position cpos are complete
+        if (kLinked) {                                            // this CTA's frames of chain position cpos are complete
             __threadfence();
             const uint32_t before = atomicAdd(c_fin + cpos, 1u);
+            if (kPipe && before == gridDim.x - 1) st_release_gpu(args.pslot, args.pseq);   // every CTA is done with the snapshot slot
             // The grid must not COMPLETE before its predecessor grid has (whatever follows the chain in the stream sees all of
             // it).  ONE resident thread is enough for that -- the last CTA out; if every CTA waited here, each would hold its
             // SM slot and shared memory until the predecessor's completion flush, delaying the launch after this one.
@@ -675,6 +737,105 @@ __global__ void __launch_bounds__(128) cw_delta_kernel(const CwConfig cfg, const
     }
 }
 
+// Pipelined host transport (cw_host.cu, device consumer, small batches): the STEP half.  A host-driven closed loop needs
+// reward / done of step k before it can issue step k+1 -- a latency problem -- while the frames are a bandwidth problem; a launch
+// that does both only reports the last world when its last CTA has found an SM slot, i.e. when the previous launch's frames are
+// out.  So the step runs here, one thread per world on its own stream: status byte to the host first, then the state that the
+// render launch of this step (cw_env_kernel<V_PIPE>, another stream) needs is copied into a SNAPSHOT slot -- the grid rows of the
+// warp's 32 worlds are one contiguous block -- and published per CTA with a release.  Live state belongs to this kernel alone,
+// so step k+1 never waits for frames; a slot is reused only after the render launch that read it has finished (`slot_free`).
+// One WARP per CTA: a step CTA must find room on an SM that is full of render CTAs which may be spinning on its result (4 x 160
+// threads x <= 96 registers leave 4096 registers: 32 threads x <= 128).  cw_host.cu keeps the two launch configurations in step.
+constexpr int kSnapThreads = 32;
+template <bool kInParams>
+__global__ void __launch_bounds__(kSnapThreads, 16) cw_step_snap_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
+                                                                        const __grid_constant__ ActionBlock pa, uint8_t* __restrict__ status,
+                                                                        const PipeSnap snap, uint32_t* __restrict__ epoch, uint32_t seq,
+                                                                        const uint32_t* slot_free, uint32_t slot_want,
+                                                                        unsigned long long* stats, int flags) {
+    __shared__ uint32_t s_obj[8];
+    // Consecutive step launches are linked by dataflow too: a dependent launch in a stream starts 5-6 us after its predecessor has
+    // COMPLETED (section 3.2), and this kernel's tail -- re-seeds, the snapshot copy -- is longer than its step.  A warp steps
+    // the same 32 worlds in every launch, so it waits for ONE word: its own mark of the step before.
+    CW_SSTAMP(0);
+    pdl_launch_dependents();
+    const int lane = lane_id();
+    const int64_t n = (int64_t)blockIdx.x * kSnapThreads + lane;
+    const bool valid = n < st.n;
+    const int64_t nn = valid ? n : 0;
+    const int cs = cfg.cell_stride;
+    uint32_t* const my_epoch = epoch + blockIdx.x;
+    if (lane == 0) chain_wait_seq(my_epoch, seq - 1u);           // (acquire: also drops this SM's stale L1 lines)
+    __syncwarp();
+    CW_SSTAMP(1);
+    uint32_t agent = 0, goal = 0, ep = 0, gag = 0, mflags = 0;
+    int t = 0;
+    bool dn = false;
+    if (valid) {
+        const int a = kInParams ? pa.a[n] : actions[n];
+        agent = __ldcg(st.agent + n); goal = __ldcg(st.goal + n); t = __ldcg(st.t + n);
+        ep = (flags & CW_F_AUTO_RESET) ? __ldcg(st.episode + n) : 0u;
+        int wcell, wval;
+        const int rew = step_core<true>(cfg, st.grid + nn * cs, st.init_grid + nn * cs, agent, goal, t, a, dn, wcell, wval);
+        if (rew > 1 << 30) CW_SSTAMP(15);                         // (never: keeps the stamp below behind the step's loads)
+        CW_SSTAMP(2);
+        // (st.wt: through the L2 to system memory now, see cw_env_kernel)
+        __stwt(status + n, (uint8_t)(0x80u | (rew == cfg.max_steps ? 2u : 0u) | (dn ? 1u : 0u)));
+        if (dn && (flags & CW_F_AUTO_RESET)) {
+            if (stats) stats_add(cfg, stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
+        } else {
+            st.agent[n] = agent; st.goal[n] = goal; st.t[n] = t;
+        }
+    }
+    uint32_t m = (flags & CW_F_AUTO_RESET) ? __ballot_sync(0xffffffffu, valid && dn) : 0u;   // finished worlds, re-seeded by the whole warp
+    // the slot's previous reader (the render launch kPipeSlots steps back) must be done with it before anything is written there
+    CW_SSTAMP(3);
+    if (slot_want) {
+        if (lane == 0) chain_wait_seq(slot_free, slot_want);
+        __syncwarp();
+    }
+    CW_SSTAMP(4);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t env = __shfl_sync(0xffffffffu, n, src);
+        const uint32_t env_ep = __shfl_sync(0xffffffffu, ep, src);
+        WarpPhilox rng;
+        Sparse8 objs;
+        uint32_t ag, gl;
+        reset_warp(cfg, st, env, nullptr, rng, ag, gl, env_ep, &objs, s_obj);   // ray.py:156-218
+        if (lane == 0) { st.agent[env] = ag; st.goal[env] = gl; st.t[env] = 0; if (st.init_agent) st.init_agent[env] = ag; }
+        uint32_t g2 = ag;
+        imagine_fresh(cfg, objs, g2, gl >> 16, rng);              // desired_goal = imagine_obs(): ray.py:191, 220-299
+        tile_from_objects(objs, cs >> 4, snap.goal + env * cs);
+        if (lane == src) { agent = ag; gag = g2; mflags = 1u | ((uint32_t)min(t, 255) << 8); }
+    }
+    if (valid) snap.meta[n] = make_uint4(agent, gag, mflags, 0u);
+    __syncwarp();                                                 // the lanes' writes (step cell, re-seeded rows) are ordered before the copy
+    {                                                             // the grid rows of the warp's 32 worlds are one contiguous block
+        const int64_t w0 = n - lane;
+        const int cnt = (int)max((int64_t)0, min((int64_t)32, st.n - w0));
+        const uint4* src = reinterpret_cast<const uint4*>(st.grid + w0 * cs);
+        uint4* dst = reinterpret_cast<uint4*>(snap.grid + w0 * cs);
+        const int nq = cnt * (cs >> 4);
+        for (int i0 = lane; i0 < nq; i0 += 32 * 8) {              // eight 16-byte loads in flight per lane (a load-store loop pays
+            uint4 v[8];                                           //  one L2 round trip per iteration: 5.6 us for 28 of them, measured)
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (i0 + 32 * u < nq) v[u] = __ldcg(src + i0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (i0 + 32 * u < nq) dst[i0 + 32 * u] = v[u];
+        }
+    }
+    // live state final, copied (the next step will write into these rows) and the snapshot of these 32 worlds complete: ONE mark
+    // for both waiters, the same warp of the next step launch and the render launch of this step
+    __syncwarp();
+    CW_SSTAMP(5);
+    if (lane == 0) { __threadfence(); st_release_gpu(my_epoch, seq); }
+    CW_SSTAMP(6);
+    pdl_wait();                                                   // grids still complete in stream order (a stream sync means what it says)
+    CW_SSTAMP(7);
+}
+
 // ---- observation-format expanders (one-hot state, AltObs frames): staged in shared memory, streamed out by TMA ------
 // Both outputs are contiguous over (world, ...), so a work item is a contiguous BYTE RANGE of the output: it is composed
 // in shared memory at the same address phase (mod 16) as its destination; the 16-byte aligned body leaves with ONE TMA
@@ -934,7 +1095,7 @@ __global__ void __launch_bounds__(128) cw_frame_policy_kernel(const uint4* __res
 // ------------------------------------------------------------------------------------------------------
 struct OccEntry { size_t smem; int per_sm; };
 struct KernelInfo { bool attr_set = false; int max_dyn = 0; int n_occ = 0; OccEntry occ[64]; };   // per kernel instantiation
-struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool alt_attr_set = false; KernelInfo k[3]; };
+struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; bool alt_attr_set = false; KernelInfo k[4]; };
 static DeviceInfo g_dev[64];
 static std::mutex g_dev_mu;   // guards the per-device attribute / occupancy cache (entry points may be called from several host threads)
 
@@ -1021,8 +1182,9 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     int rc = device_info(&dev);
     if (rc) return rc;
     if (st->n <= 0) return 0;
-    const int variant = args.chain ? V_CHAINED : (args.list ? V_LIST : V_PLAIN);
-    auto kern = variant == V_CHAINED ? cw_env_kernel<V_CHAINED> : (variant == V_LIST ? cw_env_kernel<V_LIST> : cw_env_kernel<V_PLAIN>);
+    const int variant = args.pepoch ? V_PIPE : (args.chain ? V_CHAINED : (args.list ? V_LIST : V_PLAIN));
+    auto kern = variant == V_PIPE ? cw_env_kernel<V_PIPE>
+                                  : (variant == V_CHAINED ? cw_env_kernel<V_CHAINED> : (variant == V_LIST ? cw_env_kernel<V_LIST> : cw_env_kernel<V_PLAIN>));
     KernelInfo* ki = &dev->k[variant];
     std::unique_lock<std::mutex> lk(g_dev_mu);
     if (!ki->attr_set) {   // once per device: allow any dynamic size up to the opt-in maximum, prefer shared memory
@@ -1055,6 +1217,11 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     if (args.first_split < 1) args.first_split = 1;
     const size_t ring = needs_frame ? (size_t)F * 48 * cfg->W * args.bands_per_chunk : 0;
     const int cap = tunables().ctas_per_sm > 0 ? tunables().ctas_per_sm : args.ctas_cap;
+    // Pipelined launches spin on words that a step launch on ANOTHER stream publishes: that launch must always find room, whatever
+    // mix of render launches is resident.  The register file guarantees it: at most 4 render CTAs per SM (launch bounds; 5 warps x
+    // <= 96 registers each -- with more per thread only three fit) leave >= 4096 registers, one 32-thread step CTA of <= 128.
+    const size_t min_smem = 0;
+    auto smem_for = [&](int G) { const size_t s = 3 * (size_t)G * cfg->cell_stride + ring; return s < min_smem ? min_smem : s; };
     // group size G: the per-SM critical path is (CTA waves) x G worlds; pick the G that minimises it
     int bestG = 0, best_per_sm = 1;
     int64_t best_cost = 0;
@@ -1062,7 +1229,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     const int gmax = 16384 / cfg->cell_stride < 1 ? 1 : (16384 / cfg->cell_stride > 16 ? 16 : 16384 / cfg->cell_stride);
     for (int G = (forcedG > 0 ? forcedG : 1); G <= (forcedG > 0 ? forcedG : gmax); G++) {
         if (G > 32) break;
-        const size_t smem = 3 * (size_t)G * cfg->cell_stride + ring;
+        const size_t smem = smem_for(G);
         if (smem > (size_t)ki->max_dyn) break;
         int per_sm = 0;
         for (int i = 0; i < ki->n_occ; i++)
@@ -1083,7 +1250,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     lk.unlock();
     if (bestG == 0) return CW_E_BADCONFIG;
     args.group = bestG;
-    const size_t smem = 3 * (size_t)bestG * cfg->cell_stride + ring;
+    const size_t smem = smem_for(bestG);
     int64_t blocks = (int64_t)dev->sms * best_per_sm;
     const int64_t groups = (st->n + bestG - 1) / bestG;
     if (blocks > groups) blocks = groups;                         // (work-list launch: the count lives on the device; groups == n)
@@ -1140,6 +1307,49 @@ int step_render_chained_notify(const CwConfig* cfg, const CwState* st, const uin
     // the next launch (measured at 4096 worlds, K = 128 stream launches: 15.5 -> 13.6 us per step).
     if (status && st->n <= 16384) a.ctas_cap = 3;
     return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
+}
+
+// ---- pipelined host transport: the two launches of one step (cw_host.cu) -------------------------------------------------------
+int step_snap_launch(const CwConfig* cfg, const CwState* st, const uint8_t* actions_dev, const uint8_t* actions_host, uint8_t* status,
+                     const PipeSnap* snap, uint32_t* epoch, uint32_t seq, const uint32_t* slot_free, uint32_t slot_want,
+                     int64_t* stats, int flags, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    rc = check_state(st); if (rc) return rc;
+    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
+    if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
+    if (st->n == 0) return 0;
+    if ((!actions_dev && !actions_host) || !status || !snap || !snap->grid || !snap->meta || !snap->goal || !epoch || !slot_free) return CW_E_NULLPTR;
+    if (st->goal_grid) return CW_E_BADCONFIG;
+    const int64_t blocks = (st->n + kSnapThreads - 1) / kSnapThreads;
+    cudaError_t le;
+    if (actions_host && st->n <= kParamActions) {                 // small batch: the actions travel in the kernel parameters
+        static thread_local ActionBlock blk;
+        memcpy(blk.a, actions_host, (size_t)st->n);
+        le = launch_pdl(cw_step_snap_kernel<true>, dim3((unsigned)blocks), dim3(kSnapThreads), 0, (cudaStream_t)stream, *cfg, *st, actions_dev, blk, status,
+                        *snap, epoch, seq, slot_free, slot_want, (unsigned long long*)stats, flags);
+    } else {
+        if (!actions_dev) return CW_E_NULLPTR;
+        static const ActionBlock none = {};
+        le = launch_pdl(cw_step_snap_kernel<false>, dim3((unsigned)blocks), dim3(kSnapThreads), 0, (cudaStream_t)stream, *cfg, *st, actions_dev, none, status,
+                        *snap, epoch, seq, slot_free, slot_want, (unsigned long long*)stats, flags);
+    }
+    return (int)(le != cudaSuccess ? le : cudaGetLastError());
+}
+
+int render_pipe_launch(const CwConfig* cfg, int64_t n, const PipeSnap* snap, uint8_t* obs, uint8_t* goal_obs, uint32_t* chain, int chain_pos,
+                       int obs_ring, const uint32_t* epoch, uint32_t seq, uint32_t* slot_free, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    if (n < 0 || chain_pos < 0 || chain_pos >= CW_CHAIN_MAX_POS || obs_ring < 1) return CW_E_BADCONFIG;
+    if (n == 0) return 0;
+    if (!snap || !snap->grid || !snap->meta || !snap->goal || !obs || !chain || !epoch || !slot_free) return CW_E_NULLPTR;
+    CwState st = {};
+    st.n = n;
+    EnvArgs a = {};
+    a.obs = obs; a.goal_obs = goal_obs; a.rgrid = snap->grid; a.mode = M_RENDER;
+    a.pmeta = snap->meta; a.pgoal = snap->goal; a.pepoch = epoch; a.pslot = slot_free; a.pseq = seq;
+    a.chain = chain; a.chain_pos = chain_pos; a.chain_ring = obs_ring;
+    a.ctas_cap = 3;
+    return launch_env_kernel(cfg, &st, a, (cudaStream_t)stream);
 }
 
 }  // namespace cw

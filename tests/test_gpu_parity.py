@@ -560,7 +560,8 @@ def test_randomized_configurations_vs_oracle(cw):
             native.set_fixed_pool(None)
 
 
-@pytest.mark.parametrize("size,N,max_steps", [(21, 3000, 15), (7, 130, 5), (32, 700, 20), (5, 1, 3), (6, 65, 4)])
+@pytest.mark.parametrize("size,N,max_steps", [(21, 3000, 15), (7, 130, 5), (32, 700, 20), (5, 1, 3), (6, 65, 4), (21, 900, 1), (9, 2100, 2),
+                                               (21, 20000, 40)])
 def test_host_env_device_consumer_matches_oracle(cw, size, N, max_steps):
     """Device-consumer transport (return_frames=False): chained launches, reward / done land in mapped host memory and the
     call returns on ONE notification word, frames stay in HBM (two alternating buffers).  reward / done after every call and
