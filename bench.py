@@ -354,7 +354,7 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
         for k in range(W_):                                       # eager warm-up (also warms the launch path)
             env.step(tape[k % TAPE])
         torch.cuda.synchronize()
-        chain = pixels and not args.no_chain
+        chain = not args.no_chain                                 # (compact observations: cw_step_chained, launches linked per warp)
         if chain:
             env.step(tape[0], chain_pos=0)                        # warm the chained launch path outside the capture
 
@@ -394,8 +394,10 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
     rec.update(value=N * cx.world * K / (ms / 1e3), unit=UNIT, ms_per_step=ms / K, windows_ms=res["windows_ms"], rank_ms=res["rank_ms"],
                gpu_launches=K, t0=res["t0"], t1=res["t1"],
                launch=(f"CUDA graphs of <= {TAPE} steps, one launch per step"
-                       + ("; launches chained by per-group dataflow (cw_step_render_chained: open-loop action tape, step i+1 overlaps "
-                          "the draining frame stores of step i; results identical)" if chain else "")),
+                       + (("; launches chained by per-group dataflow (cw_step_render_chained: open-loop action tape, step i+1 overlaps "
+                           "the draining frame stores of step i; results identical)" if pixels else
+                           "; launches linked per warp of 32 worlds by dataflow (cw_step_chained: open-loop action tape, no launch waits "
+                           "for its predecessor grid; results identical)") if chain else "")),
                l2=(f"frames written round-robin into {ring} buffers = {ring * N * frame_bytes / 1e6:.0f} MB > 126 MB L2 (inputs larger than "
                    "L2; no flush needed)") if pixels else "state 65536 x ~0.9 KB; step kernel is latency bound",
                episodes=("kept dense: auto-reset off, worlds step past done as upstream allows" if wl["dense"] else
@@ -411,7 +413,8 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
                            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(name),
                            "algorithmic_bytes_per_env_step": B, "units_per_launch": N, "launch_us": launch_s * 1e6, "peak_source": peak_src}
     else:
-        rec["roofline"] = {"bound": "latency/issue (reported, not an HBM roofline: 32 algorithmic bytes per env-step)", "kernel": "cw_step_kernel<false>",
+        rec["roofline"] = {"bound": "latency/issue (reported, not an HBM roofline: 32 algorithmic bytes per env-step)",
+                           "kernel": "cw_step_chained_kernel" if chain else "cw_step_kernel<false>",
                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(name),
                            "algorithmic_bytes_per_env_step": B, "units_per_launch": N, "launch_us": launch_s * 1e6, "peak_source": peak_src}
 

@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 STATS_LEN = 24
 STATS_REPLICAS = 16
 MAX_SIDE = 64
@@ -18,7 +18,7 @@ F_AUTO_RESET = 1
 F_DELTA_TRANSPORT = 2
 
 # every symbol include/cw_b200.h declares (tests check the library exports exactly these)
-SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_step_render_chained", "cw_step_render_edit", "cw_step_delta", "cw_rollout", "cw_prefill_resets",
+SYMBOLS = ["cw_abi_version", "cw_error_string", "cw_reset", "cw_step", "cw_render", "cw_step_render", "cw_step_render_chained", "cw_step_chained", "cw_step_render_edit", "cw_step_delta", "cw_rollout", "cw_prefill_resets",
            "cw_imagine", "cw_frame_policy", "cw_onehot", "cw_render_alt", "cw_host_create", "cw_host_reset", "cw_host_bind_actions", "cw_host_step",
            "cw_host_step_many", "cw_host_load_state", "cw_host_stats", "cw_host_device_state", "cw_host_stream", "cw_host_fetch_frames", "cw_host_sync",
            "cw_host_destroy"]
@@ -60,6 +60,7 @@ def _declare(lib):
         "cw_step_render_edit": [cfgp, stp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp],
         "cw_step_render_chained": [cfgp, stp, vp, vp, vp, vp, vp, vp, vp, ci, vp, ci, ci, vp],
         "cw_rollout": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
+        "cw_step_chained": [cfgp, stp, vp, vp, vp, vp, ci, vp, ci, vp],
         "cw_step_delta": [cfgp, stp, vp, vp, vp, vp, ci, ci, vp],
         "cw_imagine": [cfgp, stp, vp, vp],
         "cw_prefill_resets": [cfgp, stp, vp],

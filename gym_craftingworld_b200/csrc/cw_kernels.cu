@@ -112,11 +112,14 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 __device__ int g_dbg_per_pos = 0;                  // > 0: the stamps of chain position p go to rows [p * g_dbg_per_pos, ...) (timeline of a whole chain)
 #define CW_STAMP(slot) do { if (g_dbg && (threadIdx.x == 0 || (slot) >= 8) ) g_dbg[((size_t)dbg_row0 + blockIdx.x) * 16 + (slot)] = gtimer(); } while (0)
 #define CW_WSTAMP(slot) do { if (g_dbg && (threadIdx.x & 31) == 0) g_dbg[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16 + (slot)] = gtimer(); } while (0)
+#define CW_CSTAMP(slot) do { if (g_dbg && g_dbg_per_pos > 0 && lane_id() == 0 && (int)blockIdx.x < g_dbg_per_pos) g_dbg[((size_t)cpos * g_dbg_per_pos + blockIdx.x) * 16 + (slot)] = gtimer(); } while (0)
 #define CW_SSTAMP(slot) do { if (g_dbg && (threadIdx.x & 31) == 0 && blockIdx.x < 400) g_dbg[((size_t)600 + blockIdx.x) * 16 + (slot)] = gtimer(); } while (0)
 #else
 #define CW_STAMP(slot) do { } while (0)
 #define CW_WSTAMP(slot) do { } while (0)
+#define CW_CSTAMP(slot) do { if (g_dbg && g_dbg_per_pos > 0 && lane_id() == 0 && (int)blockIdx.x < g_dbg_per_pos) g_dbg[((size_t)cpos * g_dbg_per_pos + blockIdx.x) * 16 + (slot)] = gtimer(); } while (0)
 #define CW_SSTAMP(slot) do { } while (0)
+#define CW_CSTAMP(slot) do { } while (0)
 #endif
 
 enum : int { FL_RENDER = 1, FL_FRESH = 2, FL_GOAL = 4, FL_PENDING = 8 /* reset warp has work on this world */ };
@@ -668,6 +671,99 @@ __global__ void __launch_bounds__(128, CW_STEP_MINBLOCKS) cw_step_kernel(const C
     }
 }
 
+// Compact step as a member of a CHAIN (cw_step_chained, open-loop tape, one launch per step): a dependent launch in a stream
+// starts 5-6 us after its predecessor has COMPLETED, whatever the kernels do (section 3.2) -- several times what this kernel
+// works.  A warp steps the same 32 worlds in every launch, so launch i+1 does not wait for grid i: each warp (= CTA: a held-up
+// warp then holds nothing but its own slot) waits for ONE word, its own mark of position i (release / acquire).  A finished world
+// is re-seeded from its pre-drawn record when there is one (a copy); the ~2500 dependent instructions of the NEXT record's draw
+// run AFTER the warp has published its mark, i.e. beside the successor warp's step, not in front of it.  The last CTA out waits
+// for the predecessor grid, so grids complete in stream order.
+constexpr int kChainStepThreads = 32;
+__global__ void __launch_bounds__(kChainStepThreads, 16) cw_step_chained_kernel(const CwConfig cfg, const CwState st, const uint8_t* __restrict__ actions,
+                                                                               int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                                                                               unsigned long long* stats, uint32_t* chain, uint32_t cpos,
+                                                                               int flags) {
+    CW_CSTAMP(0);
+    pdl_launch_dependents();
+    if (cpos == 0) pdl_wait();                                    // position 0 is an ordinary launch
+    uint32_t* const c_fin = chain;
+    const int lane = lane_id();
+    const int64_t n = (int64_t)blockIdx.x * kChainStepThreads + lane;
+    uint32_t* const my_epoch = chain + CW_CHAIN_MAX_POS + blockIdx.x;
+    if (cpos > 0) {
+        if (lane == 0) chain_wait_ge(my_epoch, cpos);            // (acquire: also drops this SM's stale L1 lines)
+        __syncwarp();
+    }
+    CW_CSTAMP(1);
+    const bool valid = n < st.n;
+    const int64_t nn = valid ? n : 0;
+    const bool records = st.reset_rec != nullptr && st.n_fixed == 0;
+    uint32_t agent = 0, goal = 0, ep = 0;
+    int t = 0;
+    bool dn = false;
+    if (valid) {
+        const int a = actions[n];
+        agent = __ldcg(st.agent + n); goal = __ldcg(st.goal + n); t = __ldcg(st.t + n);
+        ep = (flags & CW_F_AUTO_RESET) ? __ldcg(st.episode + n) : 0u;
+        int wcell, wval;
+        const int rew = step_core<true>(cfg, st.grid + nn * cfg.cell_stride, st.init_grid + nn * cfg.cell_stride, agent, goal, t, a, dn, wcell, wval);
+        if (reward) reward[n] = rew;
+        if (done) done[n] = dn ? 1 : 0;
+        if (dn && (flags & CW_F_AUTO_RESET)) {
+            if (stats) stats_add(cfg, stats + ((blockIdx.x >> 2) % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);   // (the replica cw_step uses)
+        } else {
+            st.agent[n] = agent; st.goal[n] = goal; st.t[n] = t;
+        }
+    }
+    CW_CSTAMP(2);
+    const uint32_t fin = (flags & CW_F_AUTO_RESET) ? __ballot_sync(0xffffffffu, valid && dn) : 0u;   // finished worlds, re-seeded by the whole warp
+    for (uint32_t m = fin; m;) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t env = __shfl_sync(0xffffffffu, n, src);
+        const uint32_t env_ep = __shfl_sync(0xffffffffu, ep, src);
+        uint32_t ag, gl;
+        bool fast = false;
+        if (records) {                                            // (see cw_step_kernel: used only if BOTH halves carry this episode's tag)
+            uint4 h = make_uint4(env_ep, 0u, 0u, 0u);
+            if (lane < 2) h = __ldcg(reinterpret_cast<const uint4*>(st.reset_rec + env * 8) + lane);
+            fast = __all_sync(0xffffffffu, h.x == env_ep);
+            if (fast) {
+                const uint32_t a1 = __shfl_sync(0xffffffffu, h.y, 0), a2 = __shfl_sync(0xffffffffu, h.z, 0), a3 = __shfl_sync(0xffffffffu, h.w, 0);
+                const uint32_t b1 = __shfl_sync(0xffffffffu, h.y, 1), b2 = __shfl_sync(0xffffffffu, h.z, 1);
+                const uint32_t cells[9] = {a2 & 0xFFFFu, a2 >> 16, a3 & 0xFFFFu, a3 >> 16, b1 & 0xFFFFu, b1 >> 16, b2 & 0xFFFFu, b2 >> 16, a1 >> 16};
+                reset_apply(cfg, st, env, nullptr, a1 & 0xFFFFu, cells, env_ep, ag, gl);
+            }
+        }
+        if (!fast) {
+            WarpPhilox rng;
+            reset_warp(cfg, st, env, nullptr, rng, ag, gl, env_ep);   // ray.py:156-218
+        }
+        if (lane == 0) { st.agent[env] = ag; st.goal[env] = gl; st.t[env] = 0; if (st.init_agent) st.init_agent[env] = ag; }
+    }
+    __syncwarp();                                                 // the lanes' writes are ordered before the mark
+    if (lane == 0) st_release_gpu(my_epoch, cpos + 1u);          // (the release is cumulative over the warp barrier: no separate fence)
+    CW_CSTAMP(3);
+    if (records) {                                                // off the chain: the draws of the re-seeded worlds' NEXT resets
+        for (uint32_t m = fin; m;) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t env = __shfl_sync(0xffffffffu, n, src);
+            const uint32_t next_ep = __shfl_sync(0xffffffffu, ep, src) + 1u;
+            WarpPhilox rng;
+            uint32_t des, cells[9];
+            reset_sample(cfg, st, env, rng, next_ep, des, cells);
+            reset_record_write(st.reset_rec + env * 8, next_ep, des, cells);
+        }
+    }
+    CW_CSTAMP(4);
+    if (lane == 0) {                                              // (only finds the last CTA out: nothing is published through this counter)
+        const uint32_t before = atomicAdd(c_fin + cpos, 1u);
+        if (cpos > 0 && before == gridDim.x - 1) pdl_wait();
+    }
+    CW_CSTAMP(5);
+}
+
 // Delta transport (cw_step_delta): one thread per world, records straight into (possibly host-mapped) memory.  The step of a
 // host-buffer call is a synchronous round trip, so what matters here is LATENCY to the records: no tile staging, no shared
 // memory, 32 CTAs at 4096 worlds; only the warps that hold a finished world pay for its re-seed (warp-cooperative Philox
@@ -830,7 +926,7 @@ __global__ void __launch_bounds__(kSnapThreads, 16) cw_step_snap_kernel(const Cw
     // for both waiters, the same warp of the next step launch and the render launch of this step
     __syncwarp();
     CW_SSTAMP(5);
-    if (lane == 0) { __threadfence(); st_release_gpu(my_epoch, seq); }
+    if (lane == 0) st_release_gpu(my_epoch, seq);                 // (the release is cumulative over the warp barrier: no separate fence)
     CW_SSTAMP(6);
     pdl_wait();                                                   // grids still complete in stream order (a stream sync means what it says)
     CW_SSTAMP(7);
@@ -1417,6 +1513,26 @@ int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, i
     }
     cudaError_t le = launch_pdl(cw_step_kernel<false>, dim3((unsigned)(blocks + refill)), dim3(128), 0, (cudaStream_t)stream, *cfg, s2, actions,
                                 reward, done, (unsigned long long*)stats, (uint8_t*)nullptr, (uint32_t*)nullptr, K, flags, (int)blocks);
+    return (int)(le != cudaSuccess ? le : cudaGetLastError());
+}
+
+int cw_step_chained(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done, int64_t* stats,
+                    int flags, uint32_t* chain, int chain_pos, void* stream) {
+    int rc = check_config(cfg); if (rc) return rc;
+    rc = check_state(st); if (rc) return rc;
+    if (flags & ~CW_F_AUTO_RESET) return CW_E_BADFLAGS;
+    if ((flags & CW_F_AUTO_RESET) && (rc = check_reset_config(cfg))) return rc;
+    if (chain_pos < 0 || chain_pos >= CW_CHAIN_MAX_POS) return CW_E_BADCONFIG;
+    if (st->n == 0) return 0;
+    if (!actions || !chain) return CW_E_NULLPTR;
+    if (tunables().no_chain) return cw_rollout(cfg, st, actions, reward, done, stats, 1, flags, stream);
+    if (chain_pos == 0) {                                         // a chain opens: clear its counters and marks
+        cudaError_t me = cudaMemsetAsync(chain, 0, sizeof(uint32_t) * (size_t)(CW_CHAIN_MAX_POS + (st->n + 31) / 32), (cudaStream_t)stream);
+        if (me != cudaSuccess) return (int)me;
+    }
+    const int64_t blocks = (st->n + kChainStepThreads - 1) / kChainStepThreads;
+    cudaError_t le = launch_pdl(cw_step_chained_kernel, dim3((unsigned)blocks), dim3(kChainStepThreads), 0, (cudaStream_t)stream, *cfg, *st, actions,
+                                reward, done, (unsigned long long*)stats, chain, (uint32_t)chain_pos, flags);
     return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
 

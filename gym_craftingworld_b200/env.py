@@ -127,6 +127,36 @@ class OneHotObs(Mapping):
         return len(self._KEYS)
 
 
+class CompactObs(Mapping):
+    """Observation dict of ``obs_mode='compact'``: zero-copy views of the device state; the two goal masks are unpacked from the
+    packed goal word ON ACCESS -- ``step`` itself must launch nothing but the step kernel (three tiny elementwise kernels per
+    step between two step launches cost more than the step: 5-6 us of a 10 us period at 65 536 worlds, measured)."""
+    _KEYS = ("observation", "agent", "desired_goal", "achieved_goal", "init_observation")
+
+    def __init__(self, env):
+        self._env = env
+
+    def __getitem__(self, k):
+        env = self._env
+        if k == "observation":
+            return env.grid_view
+        if k == "agent":
+            return env.agent
+        if k == "desired_goal":
+            return env.desired_mask
+        if k == "achieved_goal":
+            return env.achieved_mask
+        if k == "init_observation":
+            return env.init_grid
+        raise KeyError(k)
+
+    def __iter__(self):
+        return iter(self._KEYS)
+
+    def __len__(self):
+        return len(self._KEYS)
+
+
 class BatchedCraftingWorldEnv:
     """N independent CraftingWorld worlds on one GPU behind the reference's Env surface."""
 
@@ -339,8 +369,7 @@ class BatchedCraftingWorldEnv:
                     "init_observation": self.init_obs}                                      # ray.py:194-196
         if self.obs_mode == "onehot":
             return OneHotObs(self)
-        return {"observation": self.grid_view, "agent": self.agent, "desired_goal": self.desired_mask,
-                "achieved_goal": self.achieved_mask, "init_observation": self.init_grid}
+        return CompactObs(self)
 
     @property
     def observation(self):
@@ -397,19 +426,19 @@ class BatchedCraftingWorldEnv:
         """``step`` (``ray.py:301-378``) for all worlds: ``(obs dict, reward int32[N], done bool[N], info)``.
         One kernel launch; asynchronous on the current stream (CUDA-graph capturable).
 
-        ``chain_pos`` (pixel observations only) declares an OPEN-LOOP run of steps -- an action tape that exists before
+        ``chain_pos`` (pixel or compact observations) declares an OPEN-LOOP run of steps -- an action tape that exists before
         the run starts, e.g. the K steps captured into one CUDA graph: pass 0, 1, 2, ... for consecutive calls with
         nothing else enqueued on the stream in between.  Launch ``i > 0`` then follows launch ``i - 1`` by per-group
-        dataflow (``cw_step_render_chained``) instead of waiting for its whole grid, so its work overlaps the draining
-        frame stores of the previous step.  Results are identical; a closed loop (actions computed from the previous
+        dataflow (``cw_step_render_chained``; compact observations: per warp of 32 worlds, ``cw_step_chained``) instead of
+        waiting for its whole grid, so its work overlaps the draining frame stores of the previous step.  Results are identical; a closed loop (actions computed from the previous
         observation) must use ``chain_pos=None``."""
         a = self._as_actions(actions)
         if a.shape != (self.num_envs,):
             raise ValueError(f"actions must have shape ({self.num_envs},), got {tuple(a.shape)}")
-        if not self._records_fresh:
+        if not self._records_fresh and chain_pos is None:      # (never inside a chain: nothing may sit between two positions)
             self._prefill_resets()
-        if chain_pos is not None and (self.obs_mode != "pixels" or not 0 <= int(chain_pos) < _lib.CHAIN_MAX_POS):
-            raise ValueError(f"chain_pos needs obs_mode='pixels' and 0 <= chain_pos < {_lib.CHAIN_MAX_POS}")
+        if chain_pos is not None and (self.obs_mode == "onehot" or not 0 <= int(chain_pos) < _lib.CHAIN_MAX_POS):
+            raise ValueError(f"chain_pos needs obs_mode 'pixels' or 'compact' and 0 <= chain_pos < {_lib.CHAIN_MAX_POS}")
         flags = _lib.F_AUTO_RESET if self.auto_reset else 0
         with torch.cuda.device(self.device):
             if self.obs_mode == "pixels":
@@ -444,6 +473,12 @@ class BatchedCraftingWorldEnv:
             elif self.obs_mode == "onehot":       # no pixels, but resets must produce the imagined goal state
                 rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
                                               self._done_u8.data_ptr(), None, None, None, self._stats_ptr(), flags, self._stream())
+            elif chain_pos is not None:               # compact observations, open-loop run: launches linked per warp (cw_step_chained)
+                if self._chain is None:
+                    self._chain = torch.zeros(_lib.CHAIN_MAX_POS + self.num_envs, dtype=torch.int32, device=self.device)
+                rc = self._lib.cw_step_chained(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                                               self._done_u8.data_ptr(), self._stats_ptr(), flags, self._chain.data_ptr(),
+                                               int(chain_pos), self._stream())
             else:
                 rc = self._lib.cw_step(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
                                        self._done_u8.data_ptr(), self._stats_ptr(), flags, self._stream())

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define CW_ABI_VERSION 3
+#define CW_ABI_VERSION 4
 #define CW_STATS_LEN 24
 #define CW_STATS_REPLICAS 16 /* the stats buffer is int64[CW_STATS_REPLICAS][CW_STATS_LEN]: finished episodes are added to
                                 replica (block index % 16) so same-address atomics do not serialise; consumers sum the replicas */
@@ -187,6 +187,19 @@ int cw_step_delta(const CwConfig* cfg, const CwState* st, const uint8_t* actions
  * Same per-step semantics as cw_step. */
 int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
                int64_t* stats, int K, int flags, void* stream);
+
+/* cw_step for an OPEN-LOOP run of single-step launches (action tape known in advance, e.g. a CUDA graph of K steps whose rewards
+ * feed something between the launches' outputs, or a tape too long for one cw_rollout buffer): the same step per launch, but
+ * consecutive launches are linked per WARP of 32 worlds by dataflow instead of whole-grid dependencies -- a dependent launch
+ * otherwise starts 5-6 us after its predecessor completed, four times what the step itself takes.
+ *   chain      device uint32[CW_CHAIN_MAX_POS + ceil(N / 32)] (a cw_step_render_chained buffer is large enough), used only by the chain
+ *   chain_pos  0 opens a chain (an ordinary launch that also clears `chain`); i > 0: the operation immediately before it in
+ *              `stream` is position i-1 of the same chain (same cfg / state / N / flags / stats), all inputs final before it opened.
+ * reward / done (nullable) int32[N] / uint8[N] of this step.  With pre-drawn reset records (st->reset_rec; st->reset_list is not
+ * used here) a finished world is re-seeded by a copy and its NEXT record is drawn by the same warp after it has released its
+ * successor; without them it is re-seeded inline, which delays that warp only.  Results equal the same sequence of cw_step calls. */
+int cw_step_chained(const CwConfig* cfg, const CwState* st, const uint8_t* actions, int32_t* reward, uint8_t* done,
+                    int64_t* stats, int flags, uint32_t* chain, int chain_pos, void* stream);
 
 /* Draw the NEXT reset of every world into st->reset_rec (one warp per world) and empty st->reset_list: call after cw_reset,
  * cw_host-style state injection that changes episode counters, or a change of seed.  Needs both buffers and n_fixed == 0. */

@@ -31,7 +31,7 @@ def test_header_and_binding_agree():
 def test_library_exports_every_declared_symbol(lib):
     for name in declared_symbols():
         assert hasattr(lib, name), f"libcw_b200.so does not export {name}"
-    assert lib.cw_abi_version() == 3
+    assert lib.cw_abi_version() == 4
     assert lib.cw_error_string(0) == b"ok"
     assert b"NULL" in lib.cw_error_string(-2)
 

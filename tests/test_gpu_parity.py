@@ -410,8 +410,50 @@ def test_chained_steps_match_unchained(cw, N, size, max_steps, ring, K, graph):
                 assert torch.equal(env._obs_ring[b], ref._obs_ring[b]), ("frame buffer", b, rep)
 
 
+@pytest.mark.parametrize("N,size,max_steps,K,graph", [
+    (96, 5, 2, 40, True),             # tiny launches, a reset every <= 2 steps: many positions co-resident
+    (65536, 21, 30, 128, True),       # the BASELINE config-3 shape
+    (5000, 21, 300, 64, False),       # chained launches outside a graph, worlds not a multiple of 32 / 128
+    (33, 8, 1, 20, True),             # every world re-seeded in every position
+])
+def test_chained_compact_steps_match_unchained(cw, N, size, max_steps, K, graph):
+    """cw_step_chained (consecutive launches linked per warp of 32 worlds) == the same steps as ordinary cw_step launches,
+    per-step reward / done included (each position writes its own row)."""
+    acts = torch.from_numpy(np.random.RandomState(N + K).randint(0, 6, (K, N)).astype(np.uint8)).cuda()
+    kw = dict(size=(size, size), max_steps=max_steps, seed=23, obs_mode="compact")
+    ref = cw.BatchedCraftingWorldEnv(N, **kw)
+    env = cw.BatchedCraftingWorldEnv(N, **kw)
+    ref.reset(); env.reset()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        env.step(acts[0]); env.step(acts[0], chain_pos=0)
+        ref.step(acts[0]); ref.step(acts[0])
+        s.synchronize()
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for k in range(K):
+                    env.step(acts[k], chain_pos=k)
+        for rep in range(3):
+            if graph:
+                g.replay()
+            else:
+                for k in range(K):
+                    env.step(acts[k], chain_pos=k)
+            for k in range(K):
+                ref.step(acts[k])
+            s.synchronize()
+            for key in ("grid", "init_grid", "agent", "goal", "t", "episode", "reward", "done", "stats_raw"):
+                assert torch.equal(getattr(env, key), getattr(ref, key)), (key, rep)
+        env.step(acts[0]); ref.step(acts[0])                      # an ordinary step after the chain (pre-drawn records are re-drawn)
+        s.synchronize()
+        for key in ("grid", "agent", "goal", "t", "episode", "reward", "done", "stats_raw"):
+            assert torch.equal(getattr(env, key), getattr(ref, key)), key
+
+
 def test_chained_step_rejects_bad_arguments(cw):
-    env = cw.BatchedCraftingWorldEnv(8, size=(5, 5), seed=1, obs_mode="compact")
+    env = cw.BatchedCraftingWorldEnv(8, size=(5, 5), seed=1, obs_mode="onehot")
     env.reset()
     with pytest.raises(ValueError):
         env.step(torch.zeros(8, dtype=torch.uint8, device="cuda"), chain_pos=0)
