@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch of worlds: ONE fused step + auto-reset + render launch
-(cw_env_kernel) per step for the pixel workloads, one cw_step_kernel launch for the compact workload.  Worlds are
+(cw_env_kernel) per step for the pixel workloads, one cw_step_chained_kernel launch for the compact workload.  Worlds are
 sharded over ranks by global id with no data-path collective (weak scaling: per-GPU batch fixed); with N > 1 the
 24 x int64 episode-statistics vector is snapshotted on the step stream and all-reduced over NCCL on a side stream at
 a graph-replay boundary every 128 env steps (BASELINE config 4's cadence, counted across the timed windows): the
@@ -21,7 +21,8 @@ Prints ONE JSON line (rank 0):
   e2e           the same metric through the host-buffer C entry points (HostCraftingWorldEnv -> cw_host_step) with HOST
                 arrays: `e2e.value` = frames produced in HBM for a device-side consumer, actions from / reward + done
                 back to host memory every step; `e2e.host_frames_delta` additionally keeps the frames current in HOST
-                memory; `e2e.full_frame_copy` copies every frame over PCIe.
+                memory; `e2e.full_frame_copy` copies every frame over PCIe.  Wall clock, MAX over ranks, median of 3 windows
+                of >= 1000 calls after 200 untimed calls.
   roofline      the fused kernel's algorithmic bytes per launch / its mean launch duration vs the measured HBM bandwidth.
   cpu_baseline  the reference's own CraftingWorldEnvRay (oracle/_ref, installed unmodified by oracle/build_ref.py) on the
                 host cores of this box, the Python port and the C port beside it.
@@ -525,15 +526,19 @@ def e2e_legs(cx, name, K, tape):
     acts = tape.cpu().numpy()
     res = {}
 
-    def timed(fn, n_calls, steps_per_call):
-        cx.barrier()
-        h0 = time.perf_counter()
-        for k in range(n_calls):
-            fn(k)
-        henv.sync()                                               # device-consumer legs: the frames of the last step are complete
-        dt = time.perf_counter() - h0
-        mx, _ = cx.max_over_ranks([dt])
-        return N * cx.world * n_calls * steps_per_call / mx[0]
+    def timed(fn, n_calls, steps_per_call, windows=3):
+        """median of `windows` wall-clock windows (each the MAX over ranks) of n_calls calls, like `value`'s device windows"""
+        rates = []
+        for _ in range(windows):
+            cx.barrier()
+            h0 = time.perf_counter()
+            for k in range(n_calls):
+                fn(k)
+            henv.sync()                                           # device-consumer legs: the frames of the last step are complete
+            dt = time.perf_counter() - h0
+            mx, _ = cx.max_over_ranks([dt])
+            rates.append(N * cx.world * n_calls * steps_per_call / mx[0])
+        return sorted(rates)[len(rates) // 2]
 
     for variant in ("device", "delta", "frames"):
         henv = cw.HostCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=cx.local_rank, env_id_base=cx.rank * N,
@@ -542,15 +547,15 @@ def e2e_legs(cx, name, K, tape):
         henv.reset()
         henv.load_state(t=np.random.RandomState(11 + cx.rank).randint(0, args.max_steps, N))   # staggered episode clocks (as above)
         n_steps = e_steps if variant != "frames" else max(10, e_steps // 50)
-        for k in range(20 if variant != "frames" else 3):         # untimed: page-faults of the mirrors, worker threads hot
-            henv.step(acts[k])
-        v = timed(lambda k: henv.step(acts[k % TAPE]), n_steps, 1)
+        for k in range(200 if variant != "frames" else 3):        # untimed: page-faults of the mirrors, worker threads hot, host clocks up
+            henv.step(acts[k % TAPE])
+        v = timed(lambda k: henv.step(acts[k % TAPE]), n_steps, 1, windows=3 if variant != "frames" else 1)
         res[variant] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": henv.h2d_bytes_per_step, "d2h_bytes_per_step": henv.d2h_bytes_per_step,
-                        "steps": n_steps}
+                        "steps": n_steps, "windows": 3 if variant != "frames" else 1}
         if variant == "device":                                   # the same transport, 128 steps of an open-loop tape per library call
             calls = max(1, min(e_steps // TAPE, 16))
             henv.step_many(acts)
-            res["device_many"] = {"value": timed(lambda k: henv.step_many(acts), calls, TAPE), "unit": UNIT, "steps": calls * TAPE,
+            res["device_many"] = {"value": timed(lambda k: henv.step_many(acts), calls, TAPE, windows=1), "unit": UNIT, "steps": calls * TAPE,
                                   "h2d_bytes_per_step": N, "d2h_bytes_per_step": N}
         henv.close()
         cx.barrier()
