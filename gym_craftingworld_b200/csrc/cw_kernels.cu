@@ -117,7 +117,6 @@ __device__ int g_dbg_per_pos = 0;                  // > 0: the stamps of chain p
 #else
 #define CW_STAMP(slot) do { } while (0)
 #define CW_WSTAMP(slot) do { } while (0)
-#define CW_CSTAMP(slot) do { if (g_dbg && g_dbg_per_pos > 0 && lane_id() == 0 && (int)blockIdx.x < g_dbg_per_pos) g_dbg[((size_t)cpos * g_dbg_per_pos + blockIdx.x) * 16 + (slot)] = gtimer(); } while (0)
 #define CW_SSTAMP(slot) do { } while (0)
 #define CW_CSTAMP(slot) do { } while (0)
 #endif
@@ -691,7 +690,20 @@ __global__ void __launch_bounds__(kChainStepThreads, 16) cw_step_chained_kernel(
     const int64_t n = (int64_t)blockIdx.x * kChainStepThreads + lane;
     uint32_t* const my_epoch = chain + CW_CHAIN_MAX_POS + blockIdx.x;
     if (cpos > 0) {
-        if (lane == 0) chain_wait_ge(my_epoch, cpos);            // (acquire: also drops this SM's stale L1 lines)
+        // Launches run ahead of the dependency chain until the SMs are full of waiting warps; a warp whose predecessor is itself
+        // still waiting (mark two or more positions behind) polls slowly, only the next in line polls fast.
+        if (lane == 0) {
+            uint32_t v = ld_acquire_gpu(my_epoch);
+            if (v < cpos) {
+                const unsigned long long t0 = global_timer_ns();
+                for (;;) {
+                    __nanosleep(v + 1u >= cpos ? 32 : 800);
+                    v = ld_acquire_gpu(my_epoch);
+                    if (v >= cpos) break;
+                    if (global_timer_ns() - t0 > g_chain_timeout_ns) __trap();
+                }
+            }
+        }
         __syncwarp();
     }
     CW_CSTAMP(1);
@@ -1316,8 +1328,7 @@ static int launch_env_kernel(const CwConfig* cfg, const CwState* st, EnvArgs arg
     // Pipelined launches spin on words that a step launch on ANOTHER stream publishes: that launch must always find room, whatever
     // mix of render launches is resident.  The register file guarantees it: at most 4 render CTAs per SM (launch bounds; 5 warps x
     // <= 96 registers each -- with more per thread only three fit) leave >= 4096 registers, one 32-thread step CTA of <= 128.
-    const size_t min_smem = 0;
-    auto smem_for = [&](int G) { const size_t s = 3 * (size_t)G * cfg->cell_stride + ring; return s < min_smem ? min_smem : s; };
+    auto smem_for = [&](int G) { return 3 * (size_t)G * cfg->cell_stride + ring; };
     // group size G: the per-SM critical path is (CTA waves) x G worlds; pick the G that minimises it
     int bestG = 0, best_per_sm = 1;
     int64_t best_cost = 0;
@@ -1525,7 +1536,9 @@ int cw_step_chained(const CwConfig* cfg, const CwState* st, const uint8_t* actio
     if (chain_pos < 0 || chain_pos >= CW_CHAIN_MAX_POS) return CW_E_BADCONFIG;
     if (st->n == 0) return 0;
     if (!actions || !chain) return CW_E_NULLPTR;
-    if (tunables().no_chain) return cw_rollout(cfg, st, actions, reward, done, stats, 1, flags, stream);
+    // Above ~128k worlds a launch is several waves of work and throughput-bound: the ordinary kernel's 128-thread CTAs are the better
+    // geometry there (262 144 worlds: 13.8 us per launch against 15.7), and a whole-grid dependent launch is a valid chain member.
+    if (tunables().no_chain || st->n > 131072) return cw_rollout(cfg, st, actions, reward, done, stats, 1, flags, stream);
     if (chain_pos == 0) {                                         // a chain opens: clear its counters and marks
         cudaError_t me = cudaMemsetAsync(chain, 0, sizeof(uint32_t) * (size_t)(CW_CHAIN_MAX_POS + (st->n + 31) / 32), (cudaStream_t)stream);
         if (me != cudaSuccess) return (int)me;

@@ -1,5 +1,5 @@
 """Small drivers for ncu captures: each target launches ONE kernel family a few dozen times (eager launches, no graphs).
-    python tools/ncu_targets.py chained_cfg2|chained_cfg5|delta|incremental|compact|closed  [steps]"""
+    python tools/ncu_targets.py chained_cfg2|chained_cfg5|delta|incremental|compact|compact_chained|closed|pipe  [steps]"""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
@@ -47,6 +47,22 @@ elif target == "incremental":
     tape = torch.randint(0, 6, (steps, N), device=dev, dtype=torch.uint8)
     for k in range(steps):
         env.step(tape[k])
+elif target == "pipe":                                # the two-launch pipeline of the host-driven single step
+    env = cw.HostCraftingWorldEnv(4096, seed=0, return_frames=False)
+    env.reset()
+    env.load_state(t=np.random.RandomState(1).randint(0, 300, 4096))
+    acts = np.random.RandomState(0).randint(0, 6, (steps, 4096)).astype(np.uint8)
+    for k in range(steps):
+        env.step(acts[k])
+    env.sync()
+    env.close()
+elif target == "compact_chained":
+    N = 65536
+    env = cw.BatchedCraftingWorldEnv(N, seed=0, obs_mode="compact")
+    env.reset(); stagger(env)
+    tape = torch.randint(0, 6, (steps, N), device=dev, dtype=torch.uint8)
+    for k in range(steps):
+        env.step(tape[k], chain_pos=k)
 elif target == "compact":
     N = 65536
     env = cw.BatchedCraftingWorldEnv(N, seed=0, obs_mode="compact")
