@@ -310,6 +310,36 @@ class Ctx:
                 "t0": w0, "t1": w1}
 
 
+def frame_ring(args, name, main=True):
+    """number of rotating frame buffers of a pixel workload: the ring must exceed the 126 MB L2 and chained launches need >= 2"""
+    wl = WORKLOADS[name]
+    N = (args.envs or wl["envs"]) if main else wl["envs"]
+    ring = 1
+    while N * 48 * wl["size"] * wl["size"] * ring < 300e6 and ring < 64:
+        ring *= 2
+    ring = max(ring, 2)
+    if args.ring and main:
+        ring = args.ring
+    return ring
+
+
+def workload_config(args, world):
+    """`config` of the JSON line: what is measured, as a pure function of the command line -- BOTH arms print exactly this dict
+    (how each arm measures it is under `method` / `cpu_baseline.sample`)."""
+    wl = WORKLOADS[args.workload]
+    N, size = args.envs or wl["envs"], wl["size"]
+    cfg = {"workload": f"{args.workload}: {wl['desc']}", "envs_per_gpu": N, "grid": f"{size}x{size}", "obs": wl["obs"],
+           "actions": "uniform iid over the 6 actions, a pre-generated 128-step tape, cycled",
+           "parallelism": f"dp{world} (worlds sharded by global id, no data-path collective)"}
+    if wl["obs"] == "pixels":
+        ring = frame_ring(args, args.workload)
+        cfg["l2"] = (f"GPU arm: frames written round-robin into {ring} buffers = {ring * N * 48 * size * size / 1e6:.0f} MB > 126 MB L2 (inputs larger "
+                     "than L2; no flush needed); CPU reference arm: not applicable")
+    else:
+        cfg["l2"] = "GPU arm: state of 65536 worlds x ~0.9 KB, the step kernel is latency bound; CPU reference arm: not applicable"
+    return cfg
+
+
 def stagger(env, torch, seed):
     """Spread the episode clocks uniformly over [0, max_steps): every step then sees the steady-state share of time-outs and
     re-seeds (N / max_steps worlds) instead of a synchronised storm every max_steps steps."""
@@ -327,13 +357,7 @@ def pixel_or_compact_leg(cx, name, K, W_, main):
         wl["envs"] = args.envs
     N, size, pixels = wl["envs"], wl["size"], wl["obs"] == "pixels"
     frame_bytes = 48 * size * size
-    ring = 1
-    if pixels:                                                    # rotate frame buffers so the ring exceeds the 126 MB L2
-        while N * frame_bytes * ring < 300e6 and ring < 64:
-            ring *= 2
-        ring = max(ring, 2)                                       # chained launches overlap step i+1 with the stores of step i
-        if args.ring and main:
-            ring = args.ring
+    ring = frame_ring(args, name, main) if pixels else 1          # rotate frame buffers so the ring exceeds the 126 MB L2
     auto_reset = not wl["dense"]                                  # cfg5 stays dense: a re-seed would replace a dense world by a 9-object one
     env = cw.BatchedCraftingWorldEnv(N, size=(size, size), seed=args.seed, device=cx.dev, auto_reset=auto_reset, obs_mode=wl["obs"],
                                      env_id_base=cx.rank * N, obs_buffers=ring, goal_images=not args.no_goal_images,
@@ -613,12 +637,11 @@ def run_ours(args):
             "metric": METRIC if pixels else "env-steps/sec compact obs (step kernel only)", "value": main_rec["value"], "unit": UNIT,
             "n_gpus": cx.world, "steps": K, "warmup": W_, "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": main_rec["workload"], "envs_per_gpu": main_rec["envs_per_gpu"], "grid": main_rec["grid"], "obs": main_rec["obs"],
-                       "actions": "uniform iid over 6 actions, pre-generated uint8[128,N] tape on device, cycled",
-                       "launch": main_rec["launch"], "l2": main_rec["l2"], "episodes": main_rec["episodes"],
+            "config": workload_config(args, cx.world),
+            "method": {"launch": main_rec["launch"], "l2": main_rec["l2"], "episodes": main_rec["episodes"],
+                       "actions": "the tape is a uint8[128,N] tensor on the device",
                        "timing": "exactly K steps between two CUDA events on the launching stream, behind a ~0.3 ms device-side gate so that every "
                                  "launch is queued before the start event; median of len(windows_ms) such windows, each MAX over ranks",
-                       "parallelism": f"dp{cx.world} (worlds sharded by global id, no data-path collective)",
                        "host_affinity_rank0": cx.numa},
             "windows_ms": main_rec["windows_ms"], "rank_ms": main_rec["rank_ms"], "stats_allreduce": main_rec["stats_allreduce"],
             "clocks": sampler.summary(t0, t1, t_load0) if sampler else None,
@@ -658,11 +681,15 @@ def run_reference(args):
             "Python/NumPy port of the reference (oracle/pyenv.py) -- oracle/_ref is absent on this box")
     sample = (f"{procs} processes x {per_proc} worlds, one step = every world stepped once ({procs * per_proc} env-steps), "
               f"{wl['size']}x{wl['size']} nine-skill env loop with reset on done; {what}")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-            "steps": K, "warmup": W_, "ms_per_step": 1e3 * procs * per_proc / value, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']}", "grid": f"{wl['size']}x{wl['size']}",
-                       "sample": "bounded CPU sample of the same env config (see cpu_baseline.sample)"},
+    world = max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus)
+    pixels = wl["obs"] == "pixels"
+    line = {"impl": "reference", "metric": METRIC if pixels else "env-steps/sec compact obs (step kernel only)", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": 1e3 * procs * per_proc / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, world),
+            "method": {"launch": "no GPU: one Python process per host core, each stepping its worlds one env.step() at a time (rank 0 only)",
+                       "sample": "bounded CPU sample of the same env config (see cpu_baseline.sample)",
+                       "timing": "wall clock around K steps of every world of the sample, after W warm-up steps"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
