@@ -368,7 +368,8 @@ int cw_host_create(const CwConfig* cfg, int64_t n, int device, uint64_t seed, ui
     TRY(cudaMalloc(&e->d_chain, chain_words * 4));
     // pipelined single steps: worth it where a step is a latency problem (one CTA wave of frames), i.e. for small batches
     const char* pipe_env = getenv("CW_HOST_PIPE");
-    e->pipe_ok = !(flags & CW_F_DELTA_TRANSPORT) && n <= 16384 && !(pipe_env && *pipe_env == '0');
+    const char* nochain_env = getenv("CW_NO_CHAIN");              // (debugger / sanitizer sessions: no launch may spin on another)
+    e->pipe_ok = !(flags & CW_F_DELTA_TRANSPORT) && n <= 16384 && !(pipe_env && *pipe_env == '0') && !(nochain_env && *nochain_env == '1');
     const size_t pipe_words = (size_t)cw::kPipeSlots + (size_t)((n + 31) / 32);
     if (e->pipe_ok) {
         const size_t per_slot = 2 * gb + (size_t)n * sizeof(uint4);
