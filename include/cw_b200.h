@@ -232,12 +232,14 @@ int cw_render_alt(const CwConfig* cfg, const uint8_t* grid, const uint32_t* agen
  * (ray.py:301-378) for N worlds.  Calls on one handle are not re-entrant (like the reference env object).
  *
  * Where the frames go is chosen per handle / per call:
- *   obs_host == NULL            DEVICE CONSUMER: the fused step + auto-reset + render kernel leaves the frames in HBM (two
- *                               alternating buffers, cw_host_device_state); only actions (in) and reward / done (out) cross
- *                               PCIe, through mapped pinned memory (one status byte per world comes back).  Launches are chained
- *                               (cw_step_render_chained) and the call returns as soon as every world's reward / done is in host
- *                               memory -- the frames of this step may still be draining on the handle's stream (cw_host_stream;
- *                               cw_host_sync waits for them).
+ *   obs_host == NULL            DEVICE CONSUMER: the frames are produced in HBM (rotating buffers, cw_host_device_state); only
+ *                               actions (in) and reward / done (out) cross PCIe, through mapped pinned memory (one status byte
+ *                               per world comes back).  The call returns as soon as every world's reward / done is in host
+ *                               memory -- the frames of this step may still be on their way on the handle's stream
+ *                               (cw_host_stream; cw_host_sync waits for them).  Up to 16 384 worlds a step is two launches on two
+ *                               streams (a thread-per-world step launch, and the render launch of the state snapshot it
+ *                               publishes), so step k+1 never waits for the frames of step k; larger batches and cw_host_step_many
+ *                               use one fused launch per step, chained (cw_step_render_chained).
  *   CW_F_DELTA_TRANSPORT handle HOST FRAMES by delta records: obs_host (and the goal buffer given to cw_host_reset) are
  *                               persistent mirrors owned by the caller, pass the same pointers every call; the library patches
  *                               them in place from 16-byte records (a different obs pointer triggers one full refresh).  After
@@ -268,7 +270,11 @@ int cw_host_load_state(CwHostEnv* env, const uint8_t* grid_host, const uint32_t*
                        const int32_t* t_host, uint8_t* obs_host /*nullable*/);
 int cw_host_stats(CwHostEnv* env, int64_t* stats_host /*[CW_STATS_LEN]*/);
 /* device pointers of the handle's state and of the frame buffer holding the CURRENT observation, for callers that DO have a
- * device-side consumer (e.g. a policy): order the consumer after the env kernels through cw_host_stream (a cudaStream_t) */
+ * device-side consumer (e.g. a policy): order the consumer after the env kernels through cw_host_stream (a cudaStream_t, the
+ * stream the frames are written on).  The frame buffer is one of four that rotate: work enqueued on that stream before the next
+ * cw_host_step reads complete frames of this step, and the buffer is not written again for three more steps.  The STATE arrays are
+ * advanced by the next cw_host_step as soon as it is called (small batches step on a second stream of the handle): read them
+ * between cw_host_sync and the next step. */
 int cw_host_device_state(CwHostEnv* env, CwState* out_state, uint8_t** out_obs);
 int cw_host_stream(CwHostEnv* env, void** out_stream);
 /* copy the CURRENT device frames (and the goal frames) to host memory, each nullable; synchronises the handle's stream.
