@@ -76,7 +76,11 @@ def test_argument_errors_are_codes_not_crashes(lib):
     st.n = 4
     assert lib.cw_step_render_chained(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 0, None, 0, 1, None) == -2
     assert lib.cw_step_render_edit(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 0, None, None) == -2
+    assert lib.cw_step_chained(C.byref(cfg), C.byref(st), None, None, None, None, 0, None, 0, None) == -2
     st.n = 0
+    assert lib.cw_step_chained(C.byref(cfg), C.byref(st), None, None, None, None, 0, None, 1024, None) == -1     # position out of range
+    assert lib.cw_step_chained(C.byref(cfg), C.byref(st), None, None, None, None, 6, None, 0, None) == -3
+    assert lib.cw_step_chained(C.byref(cfg), C.byref(st), None, None, None, None, 1, None, 5, None) == 0         # empty batch: no-op
     assert lib.cw_step_render_chained(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 0, None, 1024, 1, None) == -1
     assert lib.cw_step_render_chained(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 0, None, 0, 0, None) == -1
     assert lib.cw_step_render_edit(C.byref(cfg), C.byref(st), None, None, None, None, None, None, None, 2, None, None) == -3
