@@ -717,8 +717,6 @@ static int host_step_pipe(CwHostEnv* e, const uint8_t* act_host, const uint8_t* 
     }
     const auto t_launched = std::chrono::steady_clock::now();
     if (e->trace) e->tr_mid += std::chrono::duration<double, std::micro>(t_mid - t_begin).count();
-    static const bool open_loop = getenv("CW_PIPE_OPENLOOP") && *getenv("CW_PIPE_OPENLOOP") == '1';   // (experiment: GPU-side rate of the pipe)
-    if (!open_loop)
     rc = collect_status(e->h_status, n, e->cfg.max_steps, reward_host, done_host, e->s_step, e->pending_lines.data(),
                         e->trace ? &e->tr_first_byte : nullptr);
     if (rc) return rc;

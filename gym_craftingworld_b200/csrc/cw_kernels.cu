@@ -885,7 +885,6 @@ __global__ void __launch_bounds__(kSnapThreads, 16) cw_step_snap_kernel(const Cw
         ep = (flags & CW_F_AUTO_RESET) ? __ldcg(st.episode + n) : 0u;
         int wcell, wval;
         const int rew = step_core<true>(cfg, st.grid + nn * cs, st.init_grid + nn * cs, agent, goal, t, a, dn, wcell, wval);
-        if (rew > 1 << 30) CW_SSTAMP(15);                         // (never: keeps the stamp below behind the step's loads)
         CW_SSTAMP(2);
         // (st.wt: through the L2 to system memory now, see cw_env_kernel)
         __stwt(status + n, (uint8_t)(0x80u | (rew == cfg.max_steps ? 2u : 0u) | (dn ? 1u : 0u)));

@@ -446,7 +446,9 @@ def test_chained_compact_steps_match_unchained(cw, N, size, max_steps, K, graph)
             s.synchronize()
             for key in ("grid", "init_grid", "agent", "goal", "t", "episode", "reward", "done", "stats_raw"):
                 assert torch.equal(getattr(env, key), getattr(ref, key)), (key, rep)
-        env.step(acts[0]); ref.step(acts[0])                      # an ordinary step after the chain (pre-drawn records are re-drawn)
+        obs = env.step(acts[0])[0]; ref.step(acts[0])             # an ordinary step after the chain
+        assert isinstance(obs, cw.env.CompactObs)                 # lazy views: step() itself must launch nothing but the step kernel
+        assert torch.equal(obs["desired_goal"], (ref.goal >> 16) & 0xFFFF) and torch.equal(obs["achieved_goal"], ref.goal & 0xFFFF)
         s.synchronize()
         for key in ("grid", "agent", "goal", "t", "episode", "reward", "done", "stats_raw"):
             assert torch.equal(getattr(env, key), getattr(ref, key)), key
