@@ -140,7 +140,7 @@ enum : int { BAR_COMPOSE = 1, BAR_RESET_DONE = 2 };
 // ordinary launch is exactly what it was -- the extra control flow measurably slowed it (6 % at 131072 worlds) when all
 // shared one kernel body.
 // V_PIPE (pipelined host transport, section 3.6): a render-only member of a chain.  The state it renders is the SNAPSHOT a
-// cw_step_snap_kernel launch on another stream published (per 128 worlds, release / acquire), so it never waits for a grid and
+// cw_step_snap_kernel launch on another stream published (per 32 worlds, release / acquire), so it never waits for a grid and
 // nothing waits for it except the snapshot slot's next user and the frame buffer's next writer.
 enum : int { V_PLAIN = 0, V_CHAINED = 1, V_LIST = 2, V_PIPE = 3 };
 template <int kVariant>
@@ -670,9 +670,9 @@ __global__ void __launch_bounds__(128, CW_STEP_MINBLOCKS) cw_step_kernel(const C
     }
 }
 
-// Compact step as a member of a CHAIN (cw_step_chained, open-loop tape, one launch per step): a dependent launch in a stream
-// starts 5-6 us after its predecessor has COMPLETED, whatever the kernels do (section 3.2) -- several times what this kernel
-// works.  A warp steps the same 32 worlds in every launch, so launch i+1 does not wait for grid i: each warp (= CTA: a held-up
+// Compact step as a member of a CHAIN (cw_step_chained, open-loop tape, one launch per step): an ordinary launch waits for its
+// whole predecessor grid -- the slowest warp's re-seed, the refill CTAs -- plus a 2-3 us hand-over (section 3.2), together more
+// than twice the 2.6 us of stepping.  A warp steps the same 32 worlds in every launch, so launch i+1 does not wait for grid i: each warp (= CTA: a held-up
 // warp then holds nothing but its own slot) waits for ONE word, its own mark of position i (release / acquire).  A finished world
 // is re-seeded from its pre-drawn record when there is one (a copy); the ~2500 dependent instructions of the NEXT record's draw
 // run AFTER the warp has published its mark, i.e. beside the successor warp's step, not in front of it.  The last CTA out waits
@@ -862,8 +862,8 @@ __global__ void __launch_bounds__(kSnapThreads, 16) cw_step_snap_kernel(const Cw
                                                                         const uint32_t* slot_free, uint32_t slot_want,
                                                                         unsigned long long* stats, int flags) {
     __shared__ uint32_t s_obj[8];
-    // Consecutive step launches are linked by dataflow too: a dependent launch in a stream starts 5-6 us after its predecessor has
-    // COMPLETED (section 3.2), and this kernel's tail -- re-seeds, the snapshot copy -- is longer than its step.  A warp steps
+    // Consecutive step launches are linked by dataflow too: a dependent launch would wait for its predecessor's COMPLETION, and
+    // this kernel's tail -- re-seeds, the snapshot copy, the grid hand-over (section 3.2) -- is longer than its step.  A warp steps
     // the same 32 worlds in every launch, so it waits for ONE word: its own mark of the step before.
     CW_SSTAMP(0);
     pdl_launch_dependents();

@@ -191,7 +191,7 @@ int cw_rollout(const CwConfig* cfg, const CwState* st, const uint8_t* actions, i
 /* cw_step for an OPEN-LOOP run of single-step launches (action tape known in advance, e.g. a CUDA graph of K steps whose rewards
  * feed something between the launches' outputs, or a tape too long for one cw_rollout buffer): the same step per launch, but
  * consecutive launches are linked per WARP of 32 worlds by dataflow instead of whole-grid dependencies -- a dependent launch
- * otherwise starts 5-6 us after its predecessor completed, four times what the step itself takes.
+ * otherwise waits for its predecessor's slowest warp and refill CTAs plus a 2-3 us grid hand-over, more than the step itself takes.
  *   chain      device uint32[CW_CHAIN_MAX_POS + ceil(N / 32)] (a cw_step_render_chained buffer is large enough), used only by the chain
  *   chain_pos  0 opens a chain (an ordinary launch that also clears `chain`); i > 0: the operation immediately before it in
  *              `stream` is position i-1 of the same chain (same cfg / state / N / flags / stats), all inputs final before it opened.
