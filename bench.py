@@ -619,7 +619,9 @@ def run_ours(args):
         for name in ("cfg3", "cfg4", "cfg5"):
             if name == args.workload:
                 continue
-            rec, _ = pixel_or_compact_leg(cx, name, k_sub, 3, False)
+            # (a compact step launch is ~5 us: 20 of them are a 0.1 ms window, a third of it ramp -- the compact sub-record
+            #  times at least one full 128-step graph, still under a millisecond)
+            rec, _ = pixel_or_compact_leg(cx, name, max(k_sub, TAPE) if WORKLOADS[name]["obs"] == "compact" else k_sub, 3, False)
             for key in ("t0", "t1"):
                 rec.pop(key, None)
             others[name] = rec
