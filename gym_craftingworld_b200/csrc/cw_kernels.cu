@@ -1665,7 +1665,11 @@ int cw_frame_policy(const CwConfig* cfg, const uint8_t* obs, int64_t n, uint8_t*
     if ((uintptr_t)obs & 15u) return CW_E_BADCONFIG;
     DeviceInfo* dev;
     rc = device_info(&dev); if (rc) return rc;
-    const int64_t blocks = n < (int64_t)dev->sms * 16 ? n : (int64_t)dev->sms * 16;
+    // every CTA gets the same number of worlds (4096 worlds on 2368 resident CTAs would give half of them two worlds and the
+    // other half one: the launch then lasts two worlds with half the GPU idle in the second)
+    const int64_t cap = (int64_t)dev->sms * 16;
+    const int64_t per_cta = (n + cap - 1) / cap;
+    const int64_t blocks = (n + per_cta - 1) / per_cta;
     cudaError_t le = launch_pdl(cw_frame_policy_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream,
                                 reinterpret_cast<const uint4*>(obs), n, (uint32_t)(3 * cfg->H * cfg->W), actions);
     return (int)(le != cudaSuccess ? le : cudaGetLastError());
