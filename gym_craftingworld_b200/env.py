@@ -127,6 +127,19 @@ class OneHotObs(Mapping):
         return len(self._KEYS)
 
 
+class _NoGuard:
+    """``with`` target when the env's device is already current (``torch.cuda.device(...)`` costs 3-4 us per use)."""
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)     # the current stream's handle without building a Stream object
+
+
 class CompactObs(Mapping):
     """Observation dict of ``obs_mode='compact'``: zero-copy views of the device state; the two goal masks are unpacked from the
     packed goal word ON ACCESS -- ``step`` itself must launch nothing but the step kernel (three tiny elementwise kernels per
@@ -188,6 +201,7 @@ class BatchedCraftingWorldEnv:
             raise RuntimeError("gym_craftingworld_b200 needs a CUDA device: there is no CPU path")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        self._dev_index = int(self.device.index)
         self.STATE_W, self.STATE_H = self.cfg.W, self.cfg.H
         self.MAX_STEPS = self.cfg.max_steps
         self.task_list, self.selected_tasks = list(task_list), list(selected_tasks)
@@ -251,6 +265,7 @@ class BatchedCraftingWorldEnv:
         self._fixed_grid = self._fixed_agent = None
         self._seed = None
         self._state = _lib.CwState()
+        self._cfg_ref, self._state_ref = C.byref(self.cfg), C.byref(self._state)   # (both structs live as long as the env: built once)
         self.seed(seed)
         self._info = GoalInfo(self)
         self._bits = torch.arange(len(self.task_list), dtype=torch.int32, device=dev)
@@ -291,12 +306,18 @@ class BatchedCraftingWorldEnv:
         pool.t, pool.episode, pool.n, pool.seed, pool.env_id_base = t.data_ptr(), ep.data_ptr(), n, self._seed, FIXED_POOL_ID_BASE
         pool.n_fixed = 0
         pool.goal_grid = pool.goal_agent = pool.init_agent = pool.reset_rec = pool.reset_list = None
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self._lib.cw_reset(C.byref(self.cfg), C.byref(pool), None, None, None, None, self._stream()), "cw_reset(pool)")
         self._fixed_grid, self._fixed_agent = g, ag
 
     def _stream(self):
+        if _raw_stream is not None:
+            return _raw_stream(self._dev_index)
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _guard(self):
+        """Device guard for a launch: a no-op when the env's device is the current one (the usual case)."""
+        return _NO_GUARD if torch.cuda.current_device() == self._dev_index else torch.cuda.device(self.device)
 
     # ---- reference-style attributes ------------------------------------------------------------------
     @property
@@ -350,7 +371,7 @@ class BatchedCraftingWorldEnv:
         out = torch.empty((self.num_envs, self.cfg.H, self.cfg.W, 12), dtype=torch.uint8, device=self.device)
         src = grid if grid is not None else (self.init_grid if init else self.grid)
         ag = agent if agent is not None else self.agent
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self._lib.cw_onehot(C.byref(self.cfg), src.data_ptr(), ag.data_ptr(), out.data_ptr(),
                                            self.num_envs, self._stream()), "cw_onehot")
         return out
@@ -389,7 +410,7 @@ class BatchedCraftingWorldEnv:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
             if m.shape != (self.num_envs,):
                 raise ValueError(f"mask must have shape ({self.num_envs},)")
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self._lib.cw_reset(C.byref(self.cfg), C.byref(self._state), self._ptr(m), self._ptr(self.obs),
                                           self._ptr(self.desired_goal), self._ptr(self.init_obs), self._stream()), "cw_reset")
         self._prefill_resets()
@@ -400,12 +421,15 @@ class BatchedCraftingWorldEnv:
     def _prefill_resets(self):
         """Draw every world's NEXT reset ahead of time (compact step path); a no-op without the record buffers."""
         if self.reset_rec is not None:
-            with torch.cuda.device(self.device):
+            with self._guard():
                 _lib.check(self._lib.cw_prefill_resets(C.byref(self.cfg), C.byref(self._state), self._stream()), "cw_prefill_resets")
         self._records_fresh = True
 
     def _as_actions(self, actions):
         a = actions
+        if (type(a) is torch.Tensor and a.dtype is torch.uint8 and a.device == self.device and a.is_contiguous()
+                and not self.validate_actions):
+            return a                                               # the usual case: a uint8 tensor on the env's device
         if not isinstance(a, torch.Tensor):
             a = torch.as_tensor(np.asarray(a).reshape(-1), device=self.device)
         if a.device != self.device:
@@ -440,7 +464,7 @@ class BatchedCraftingWorldEnv:
         if chain_pos is not None and (self.obs_mode == "onehot" or not 0 <= int(chain_pos) < _lib.CHAIN_MAX_POS):
             raise ValueError(f"chain_pos needs obs_mode 'pixels' or 'compact' and 0 <= chain_pos < {_lib.CHAIN_MAX_POS}")
         flags = _lib.F_AUTO_RESET if self.auto_reset else 0
-        with torch.cuda.device(self.device):
+        with self._guard():
             if self.obs_mode == "pixels":
                 if len(self._obs_ring) > 1:
                     self._ring_pos = (self._ring_pos + 1) % len(self._obs_ring)
@@ -450,7 +474,7 @@ class BatchedCraftingWorldEnv:
                         raise ValueError("chain_pos applies to render='full' only")
                     if self._edit_scratch is None:
                         self._edit_scratch = torch.zeros(self.num_envs + 2, dtype=torch.int32, device=self.device)
-                    rc = self._lib.cw_step_render_edit(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                    rc = self._lib.cw_step_render_edit(self._cfg_ref, self._state_ref, a.data_ptr(), self.reward.data_ptr(),
                                                        self._done_u8.data_ptr(), self.obs.data_ptr(), self._ptr(self.desired_goal),
                                                        self._ptr(self.init_obs), self._stats_ptr(), flags,
                                                        self._edit_scratch.data_ptr(), self._stream())
@@ -461,26 +485,26 @@ class BatchedCraftingWorldEnv:
                     if self._chain is None:
                         self._chain = torch.zeros(_lib.CHAIN_MAX_POS + self.num_envs, dtype=torch.int32, device=self.device)
                     rc = self._lib.cw_step_render_chained(
-                        C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(), self._done_u8.data_ptr(),
+                        self._cfg_ref, self._state_ref, a.data_ptr(), self.reward.data_ptr(), self._done_u8.data_ptr(),
                         self.obs.data_ptr(), self._ptr(self.desired_goal), self._ptr(self.init_obs), self._stats_ptr(), flags,
                         self._chain.data_ptr(), int(chain_pos), len(self._obs_ring), self._stream())
                     _lib.check(rc, "cw_step_render_chained")
                     self._obs_version += 1
                     return self._observation(), self.reward, self.done, self._info
-                rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                rc = self._lib.cw_step_render(self._cfg_ref, self._state_ref, a.data_ptr(), self.reward.data_ptr(),
                                               self._done_u8.data_ptr(), self.obs.data_ptr(), self._ptr(self.desired_goal),
                                               self._ptr(self.init_obs), self._stats_ptr(), flags, self._stream())
             elif self.obs_mode == "onehot":       # no pixels, but resets must produce the imagined goal state
-                rc = self._lib.cw_step_render(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                rc = self._lib.cw_step_render(self._cfg_ref, self._state_ref, a.data_ptr(), self.reward.data_ptr(),
                                               self._done_u8.data_ptr(), None, None, None, self._stats_ptr(), flags, self._stream())
             elif chain_pos is not None:               # compact observations, open-loop run: launches linked per warp (cw_step_chained)
                 if self._chain is None:
                     self._chain = torch.zeros(_lib.CHAIN_MAX_POS + self.num_envs, dtype=torch.int32, device=self.device)
-                rc = self._lib.cw_step_chained(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                rc = self._lib.cw_step_chained(self._cfg_ref, self._state_ref, a.data_ptr(), self.reward.data_ptr(),
                                                self._done_u8.data_ptr(), self._stats_ptr(), flags, self._chain.data_ptr(),
                                                int(chain_pos), self._stream())
             else:
-                rc = self._lib.cw_step(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self.reward.data_ptr(),
+                rc = self._lib.cw_step(self._cfg_ref, self._state_ref, a.data_ptr(), self.reward.data_ptr(),
                                        self._done_u8.data_ptr(), self._stats_ptr(), flags, self._stream())
         _lib.check(rc, "cw_step")
         self._obs_version += 1
@@ -493,7 +517,7 @@ class BatchedCraftingWorldEnv:
         obs = self.obs if obs is None else obs
         if out is None:
             out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self._lib.cw_frame_policy(C.byref(self.cfg), obs.data_ptr(), self.num_envs, out.data_ptr(), self._stream()),
                        "cw_frame_policy")
         return out
@@ -513,7 +537,7 @@ class BatchedCraftingWorldEnv:
             rew = torch.empty((K, self.num_envs), dtype=torch.int32, device=self.device)
             dn = torch.empty((K, self.num_envs), dtype=torch.uint8, device=self.device)
         flags = _lib.F_AUTO_RESET if self.auto_reset else 0
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self._lib.cw_rollout(C.byref(self.cfg), C.byref(self._state), a.data_ptr(), self._ptr(rew), self._ptr(dn),
                                             self._stats_ptr(), K, flags, self._stream()), "cw_rollout")
         return (rew, dn.view(torch.bool)) if return_trace else None
@@ -536,7 +560,7 @@ class BatchedCraftingWorldEnv:
             r, c, h = (torch.as_tensor(x, device=self.device).to(torch.int32).reshape(-1) for x in (r, c, h))
             agent = (r | (c << 8) | (h << 16)).contiguous()
             out = torch.empty((M, 4 * H, 4 * W, 3), dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self._lib.cw_render(C.byref(self.cfg), grid.data_ptr(), agent.data_ptr(), out.data_ptr(), M, self._stream()),
                        "cw_render")
         return out
@@ -590,11 +614,11 @@ class BatchedCraftingWorldEnv:
             self.render()
             if self.goal_images:
                 self.init_obs.copy_(self.obs)
-                with torch.cuda.device(self.device):
+                with self._guard():
                     _lib.check(self._lib.cw_imagine(C.byref(self.cfg), C.byref(self._state), self.desired_goal.data_ptr(),
                                                     self._stream()), "cw_imagine")
         elif self.obs_mode == "onehot":
-            with torch.cuda.device(self.device):
+            with self._guard():
                 _lib.check(self._lib.cw_imagine(C.byref(self.cfg), C.byref(self._state), None, self._stream()), "cw_imagine")
         self._is_reset = True
         self._obs_version += 1
@@ -702,7 +726,7 @@ class BatchedCraftingWorldEnvAltObs(BatchedCraftingWorldEnv):
     def render_alt(self, grid, agent):
         M = grid.shape[0]
         out = torch.empty((M, 3 * self.cfg.H + 3, 3 * self.cfg.W, 3), dtype=torch.int16, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self._lib.cw_render_alt(C.byref(self.cfg), grid.data_ptr(), agent.data_ptr(), out.data_ptr(), M,
                                                self._stream()), "cw_render_alt")
         return out
