@@ -92,3 +92,34 @@ def test_host_buffer_api_beside_the_live_reference(ray, cw):
             assert int(reward[b]) == rw and bool(done[b]) == dn, (b, t)
             assert np.array_equal(obs["observation"][b], e.obs_image.astype(np.uint8)), (b, t)
     henv.close()
+
+
+def test_pipelined_host_step_beside_the_live_reference(ray, cw):
+    """Device-consumer transport (two-launch pipeline: step launch + render launch of its snapshot) beside the live
+    reference: reward / done after every call, and the device frames -- fetched -- against the reference's obs_image."""
+    B, size, T = 40, 21, 150
+    envs = []
+    for i in range(B):
+        e = ray.CraftingWorldEnvRay(size=(size, size))
+        e.seed(300 + i)
+        e.reset()
+        envs.append(e)
+    states = [ref_shim.read_back(e) for e in envs]
+    henv = cw.HostCraftingWorldEnv(B, size=(size, size), auto_reset=False, return_frames=False)
+    henv.reset()
+    agent = np.array([s[1] | (s[2] << 8) | (s[3] << 16) for s in states], np.uint32)
+    goal = np.array([ref_shim.bits_to_mask(e.desired_goal_vector[0]) << 16 for e in envs], np.uint32)
+    henv.load_state(np.stack([s[0] for s in states]), agent, goal, np.zeros(B, np.int32))
+    assert np.array_equal(henv.fetch_frames()[0], np.stack([e.obs_image for e in envs]).astype(np.uint8))
+    rng = np.random.RandomState(9)
+    for t in range(T):
+        a = rng.randint(0, 6, B)
+        _, reward, done, _ = henv.step(a)
+        for b, e in enumerate(envs):
+            _, rw, dn, _ = e.step(int(a[b]))
+            assert int(reward[b]) == rw and bool(done[b]) == dn, (b, t)
+        if t % 5 == 4 or t == T - 1:
+            frames = henv.fetch_frames()[0]
+            for b, e in enumerate(envs):
+                assert np.array_equal(frames[b], e.obs_image.astype(np.uint8)), (b, t)
+    henv.close()
