@@ -607,9 +607,11 @@ def test_randomized_configurations_vs_oracle(cw):
 @pytest.mark.parametrize("size,N,max_steps", [(21, 3000, 15), (7, 130, 5), (32, 700, 20), (5, 1, 3), (6, 65, 4), (21, 900, 1), (9, 2100, 2),
                                                (21, 20000, 40)])
 def test_host_env_device_consumer_matches_oracle(cw, size, N, max_steps):
-    """Device-consumer transport (return_frames=False): chained launches, reward / done land in mapped host memory and the
-    call returns on ONE notification word, frames stay in HBM (two alternating buffers).  reward / done after every call and
-    the device frames (fetched) every few steps must equal the oracle's."""
+    """Device-consumer transport (return_frames=False): reward / done land in mapped host memory as one status byte per world
+    and the call returns without a stream synchronisation, frames stay in HBM (rotating buffers).  Up to 16 384 worlds a step is
+    the two-launch pipeline (step launch + render launch of its snapshot; 1- and 2-step episodes re-seed a world in consecutive
+    steps), above that one fused chained launch.  reward / done after every call and the device frames (fetched) every few
+    steps must equal the oracle's."""
     seed, K = 17, 70
     env = cw.HostCraftingWorldEnv(N, size=(size, size), max_steps=max_steps, seed=seed, return_frames=False)
     ob = native.OracleBatch(native.make_config(H=size, W=size, max_steps=max_steps), N, seed=seed)
