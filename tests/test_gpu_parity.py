@@ -532,6 +532,39 @@ def test_no_out_of_bounds_writes_guard_bands(cw, mode):
         assert np.array_equal(env.obs.cpu().numpy(), o_obs)
 
 
+def test_no_out_of_bounds_writes_guard_bands_chained_compact(cw):
+    """The same hunt for cw_step_chained (one-warp CTAs, per-warp marks, pre-drawn reset records written after the mark): odd
+    world counts, every buffer the kernel writes between guard bands."""
+    from gym_craftingworld_b200 import _lib as _l
+    GUARD = 4096
+    for size, N in ((21, 1031), (5, 77), (32, 300)):
+        env = cw.BatchedCraftingWorldEnv(N, size=(size, size), max_steps=7, seed=size, obs_mode="compact")
+        env._chain = torch.zeros(_l.CHAIN_MAX_POS + (N + 31) // 32, dtype=torch.int32, device="cuda")     # the documented minimum
+        pads = {}
+        for name in ["grid", "init_grid", "agent", "goal", "t", "episode", "reward", "_done_u8", "reset_rec", "reset_list", "init_agent", "_chain"]:
+            old = getattr(env, name)
+            nbytes = old.numel() * old.element_size()
+            raw = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
+            view = raw[GUARD:GUARD + nbytes].view(old.dtype).view(old.shape)
+            view.zero_()
+            setattr(env, name, view)
+            pads[name] = raw
+        env.done = env._done_u8.view(torch.bool)
+        env._refresh_state_struct()
+        env.reset()
+        acts = torch.randint(0, 6, (60, N), device="cuda", dtype=torch.uint8)
+        for k in range(60):
+            env.step(acts[k], chain_pos=k)
+        torch.cuda.synchronize()
+        for name, raw in pads.items():
+            assert bool((raw[:GUARD] == 0xA5).all()) and bool((raw[-GUARD:] == 0xA5).all()), f"{name} guard band hit at {size}x{size}"
+        ob = oracle_for(env, size)
+        ob.reset()
+        for k in range(60):
+            ob.step_full(acts[k].cpu().numpy(), auto_reset=True)
+        assert_env_equals_oracle(env, ob, f"guarded chained compact {size}")
+
+
 @pytest.mark.parametrize("size,N,max_steps", [(21, 3000, 15), (5, 700, 6), (32, 260, 20)])
 def test_host_env_delta_transport_matches_oracle(cw, size, N, max_steps):
     """Delta transport: the device ships 16-byte records, the host library patches the caller's pinned frame mirror.
