@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(kEnvThreads, 4) cw_env_kernel(const CwConfig c
                     }
                     if (dn && (mode & M_AUTO_RESET)) {
                         flag |= FL_PENDING;
-                        if (args.stats) stats_add(cfg, args.stats + (blockIdx.x % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
+                        // (replica chosen by the WORLD, not by the CTA: the same counts whatever the launch geometry)
+                        if (args.stats) stats_add(cfg, args.stats + ((e >> 5) % CW_STATS_REPLICAS) * CW_STATS_LEN, goal, t, rew);
                     } else {
                         st.agent[e] = agent; st.goal[e] = goal; st.t[e] = t;
                     }
@@ -1408,10 +1409,14 @@ int step_render_chained_notify(const CwConfig* cfg, const CwState* st, const uin
     a.status = status;
     if (tunables().no_chain) return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);   // (debugger / sanitizer sessions, experiments)
     a.chain = chain; a.chain_pos = chain_pos; a.chain_ring = obs_ring;
-    // Host-driven (stream-launched) chains of small batches: with 4 CTAs per SM one launch fills the GPU, and the next launch's CTAs
-    // -- whose step phases the host is waiting for -- only get SM slots as this one's leave.  3 per SM leaves room for the head of
-    // the next launch (measured at 4096 worlds, K = 128 stream launches: 15.5 -> 13.6 us per step).
-    if (status && st->n <= 16384) a.ctas_cap = 3;
+    // Chains of small batches (about one CTA wave of frames per launch): with 4 CTAs per SM one launch fills the GPU, and the next
+    // launch's CTAs only get SM slots -- and only then run their 4 us prologues -- as this one's leave, in bursts.  3 per SM leaves
+    // room for the head of the next launch.  Host-driven chains, whose step phases the host is waiting for: 15.5 -> 13.6 us per
+    // step at 4096 worlds (K = 128 stream launches).  Graph chains: the ramp of a chain that starts on an idle GPU shrinks (20-step
+    // windows at config 2: 14.2-14.9 -> 13.9-14.1 us per step, most on the slower boxes of the pool) for 1 % of the steady state
+    // (12.9 -> 13.0 us), profiles/r2_sweep_short_window.txt.
+    const double frame_total = (double)st->n * 48.0 * cfg->H * cfg->W;
+    if (st->n <= 16384 && (status || frame_total <= 256e6)) a.ctas_cap = 3;
     return launch_env_kernel(cfg, st, a, (cudaStream_t)stream);
 }
 
