@@ -709,11 +709,11 @@ static int host_step_pipe(CwHostEnv* e, const uint8_t* act_host, const uint8_t* 
     if (rc) return rc;
     const auto t_mid = std::chrono::steady_clock::now();
     if (!skip_render) {
-    e->cur = (e->cur + 1) % e->nring;
-    rc = cw::render_pipe_launch(&e->cfg, n, &e->snap[slot], e->d_obs[e->cur], e->d_goal_obs, e->d_chain, e->chain_pos, e->nring,
-                                words + cw::kPipeSlots, seq, words + slot, e->streams[0]);
-    if (rc) return rc;
-    e->chain_pos = (e->chain_pos + 1) % CW_CHAIN_MAX_POS;
+        e->cur = (e->cur + 1) % e->nring;
+        rc = cw::render_pipe_launch(&e->cfg, n, &e->snap[slot], e->d_obs[e->cur], e->d_goal_obs, e->d_chain, e->chain_pos, e->nring,
+                                    words + cw::kPipeSlots, seq, words + slot, e->streams[0]);
+        if (rc) return rc;
+        e->chain_pos = (e->chain_pos + 1) % CW_CHAIN_MAX_POS;
     }
     const auto t_launched = std::chrono::steady_clock::now();
     if (e->trace) e->tr_mid += std::chrono::duration<double, std::micro>(t_mid - t_begin).count();
