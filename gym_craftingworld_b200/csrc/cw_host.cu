@@ -1,10 +1,11 @@
 // cw_host.cu -- host-buffer API: the batched env behind an opaque handle (cw_host_*, see include/cw_b200.h).
 //
 // Every argument is a HOST pointer.  One call = one reference-style `env.step(actions)` for N worlds.  Three transports:
-//   device consumer (obs_host == NULL)   the fused step + reset + render kernel leaves the frames in HBM (a ring of two frame
-//       buffers); launches are chained by per-group dataflow, reward / done are written straight into mapped pinned host
-//       memory and the call returns when ONE mapped word says the step phase of every world is done -- no stream
-//       synchronisation, the frames of step k drain under step k+1.
+//   device consumer (obs_host == NULL)   the frames stay in HBM (a ring of four frame buffers); reward / done come back as one
+//       self-validating status byte per world in mapped pinned host memory and the call returns when all of them have landed --
+//       no stream synchronisation, the frames of step k are written behind step k+1.  Single steps of batches <= 16384 worlds:
+//       a two-launch pipeline on two streams (host_step_pipe: thread-per-world step launch + render launch of the state
+//       snapshot it publishes); larger batches and cw_host_step_many: one fused launch per step, chained by per-group dataflow.
 //   delta (CW_F_DELTA_TRANSPORT)         a thread-per-world kernel writes one pre-digested 16-byte record per world into
 //       mapped pinned memory; a small worker pool patches the <= 2 changed cells of each world in the caller's frame buffer
 //       while the kernel runs (the reference's render_edit, ray.py:522-557).  No stream synchronisation either.

@@ -8,9 +8,14 @@
 //                      V_PLAIN   ordinary launch (whole-grid dependency on the previous launch, PDL)
 //                      V_CHAINED consecutive step launches linked by per-group dataflow (cw_step_render_chained, 3.1b)
 //                      V_LIST    work-list launch: re-seed + render the worlds a preceding step launch queued (3.5)
+//                      V_PIPE    render-only member of a chain, fed by the snapshots of cw_step_snap_kernel (host path, 3.6)
 //   cw_step_kernel<E>  one thread per world, K steps per launch, warp-cooperative auto-reset; compact observations.
 //                      Bound: latency / issue (tens of bytes per world-step).  E = true: the thread also patches the
 //                      world's device frame (render_edit) and queues finished worlds instead of re-seeding them.
+//   cw_step_chained_kernel   the compact step as a member of a chain: one-warp CTAs linked per warp by release / acquire
+//                      marks (3.2).  Bound: the per-warp dependency chain (latency).
+//   cw_step_snap_kernel      the step half of the pipelined host path: status bytes, live state, a state snapshot per step (3.6)
+//   cw_delta_kernel    thread-per-world step that emits pre-digested 16-byte records for a host-side frame mirror (3.6)
 //   cw_onehot_kernel, cw_render_alt_kernel   observation-format expanders: work items staged in shared memory at the
 //                      destination's 16-byte phase, TMA bulk stores, two stages (3.4).  Bound: HBM write.
 #include <cuda_runtime.h>
