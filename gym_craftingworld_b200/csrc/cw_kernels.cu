@@ -1173,21 +1173,23 @@ __global__ void __launch_bounds__(kExpThreads) cw_render_alt_kernel(const CwConf
 // turns it into that world's next action, so step k+1 depends on frame k the way it does under a policy network.
 //   h = sum_i word_i * (2 i + 1)  (uint32 words of the frame, wrap-around),  action = ((h ^ h >> 16) & 0xFFFF) % 6
 // One CTA per world (grid-stride), 16-byte streaming loads, warp-shuffle + shared-memory reduction.  Bound: HBM read.
-__global__ void __launch_bounds__(128) cw_frame_policy_kernel(const uint4* __restrict__ obs, int64_t n, uint32_t words16,
-                                                              uint8_t* __restrict__ actions) {
-    __shared__ uint32_t s_part[4];
+constexpr int kPolicyThreads = 256, kPolicyLoads = 6;    // 256 x 6 x 16 B = one 21x21 frame (21 168 B) in ONE round of loads
+__global__ void __launch_bounds__(kPolicyThreads) cw_frame_policy_kernel(const uint4* __restrict__ obs, int64_t n, uint32_t words16,
+                                                                         uint8_t* __restrict__ actions) {
+    __shared__ uint32_t s_part[kPolicyThreads / 32];
     pdl_launch_dependents();
     pdl_wait();
     for (int64_t w = blockIdx.x; w < n; w += gridDim.x) {
         const uint4* f = obs + (size_t)w * words16;
         uint32_t h = 0;
-        for (uint32_t i0 = threadIdx.x; i0 < words16; i0 += 4 * 128) {   // four independent 16-byte loads in flight per thread
-            uint4 v[4];
+        for (uint32_t i0 = threadIdx.x; i0 < words16; i0 += kPolicyLoads * kPolicyThreads) {   // independent 16-byte loads in flight per thread
+            uint4 v[kPolicyLoads];
 #pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = (i0 + 128u * u < words16) ? __ldcs(f + i0 + 128u * u) : make_uint4(0u, 0u, 0u, 0u);
+            for (int u = 0; u < kPolicyLoads; u++)
+                v[u] = (i0 + (uint32_t)(kPolicyThreads * u) < words16) ? __ldcs(f + i0 + kPolicyThreads * u) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t k = 8u * (i0 + 128u * u) + 1u;     // 2 * (4 i) + 1
+            for (int u = 0; u < kPolicyLoads; u++) {
+                const uint32_t k = 8u * (i0 + (uint32_t)(kPolicyThreads * u)) + 1u;     // 2 * (4 i) + 1
                 h += v[u].x * k + v[u].y * (k + 2u) + v[u].z * (k + 4u) + v[u].w * (k + 6u);
             }
         }
@@ -1196,7 +1198,9 @@ __global__ void __launch_bounds__(128) cw_frame_policy_kernel(const uint4* __res
         if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = h;
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t t = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+            uint32_t t = 0;
+#pragma unroll
+            for (int q = 0; q < kPolicyThreads / 32; q++) t += s_part[q];
             actions[w] = (uint8_t)(((t ^ (t >> 16)) & 0xFFFFu) % 6u);
         }
         __syncthreads();
@@ -1677,10 +1681,10 @@ int cw_frame_policy(const CwConfig* cfg, const uint8_t* obs, int64_t n, uint8_t*
     rc = device_info(&dev); if (rc) return rc;
     // every CTA gets the same number of worlds (4096 worlds on 2368 resident CTAs would give half of them two worlds and the
     // other half one: the launch then lasts two worlds with half the GPU idle in the second)
-    const int64_t cap = (int64_t)dev->sms * 16;
+    const int64_t cap = (int64_t)dev->sms * (2048 / kPolicyThreads);
     const int64_t per_cta = (n + cap - 1) / cap;
     const int64_t blocks = (n + per_cta - 1) / per_cta;
-    cudaError_t le = launch_pdl(cw_frame_policy_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream,
+    cudaError_t le = launch_pdl(cw_frame_policy_kernel, dim3((unsigned)blocks), dim3(kPolicyThreads), 0, (cudaStream_t)stream,
                                 reinterpret_cast<const uint4*>(obs), n, (uint32_t)(3 * cfg->H * cfg->W), actions);
     return (int)(le != cudaSuccess ? le : cudaGetLastError());
 }
