@@ -200,3 +200,34 @@ def test_config4_131072_worlds_properties(cw):
     ag = env.agent.cpu().numpy()
     assert ((ag & 0xFF) < 21).all() and (((ag >> 8) & 0xFF) < 21).all() and (((ag >> 16) & 0xFF) <= 3).all()
     assert set(np.unique(env.reward.cpu().numpy())) <= {-1, 10}
+
+
+def test_bench_line_contract():
+    """`python bench.py` (our arm, shortened): ONE JSON line with the contract's keys, a roofline record that can be recomputed
+    from the line, declared e2e copy sizes, and the same `config` dict the reference arm prints."""
+    import argparse
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "bench.py", "--steps", "20", "--warmup", "5", "--only", "--quick", "--no-cpu-baseline", "--no-steady",
+                          "--no-incremental", "--no-closed-loop"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "method", "clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["steps"] == 20 and d["gpu_launches"] == 20 and d["n_gpus"] == 1 and d["dtype"] == "u8" and d["vs_baseline"] is None
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    algorithmic = r["algorithmic_bytes_per_env_step"] * r["units_per_launch"]
+    assert abs(r["achieved"] - algorithmic / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert abs(d["value"] - 4096 * 20 / (d["ms_per_step"] * 20e-3)) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 and e["d2h_bytes_per_step"] > 0
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.workload_config(argparse.Namespace(workload="cfg2", envs=0, ring=0), 1)

@@ -157,6 +157,11 @@ def test_bench_reference_arm_contract():
     installed = os.path.isfile(os.path.join(root, "oracle", "_ref", "gym_craftingworld", "envs", "craftingworld_ray.py"))
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == ("reference" if installed else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # both arms print the SAME config dict: a pure function of the command line
+    import argparse
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.workload_config(argparse.Namespace(workload="cfg2", envs=0, ring=0), 1) and "method" in d
 
 
 def test_tools_and_entry_points_compile():
